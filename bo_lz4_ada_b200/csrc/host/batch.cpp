@@ -1,0 +1,692 @@
+// batch.cpp -- the batched device entry point: block-table builder + batch scheduler.
+//
+// Host stage (lz4ada_batch_plan): every stream is walked by the same state machine that serves
+// Update (walker.cpp), with a BlockEngine that records blocks instead of decoding them.  That
+// gives header / size-word / Single_Frame errors exactly where the reference raises them
+// (lib/lz4ada.adb:155-361, 525-585) and a table {compressed offset, size, stored flag, checksum
+// flag} per block.  Nothing is decoded on the host.
+//
+// Device stage (lz4ada_batch_run): K1 over all independent blocks (one warp each), K4 over
+// linked frames (one warp per frame), K3 over the frames that carry a content checksum -- no host
+// round trip in between -- then one D2H of the status / digest arrays, folded in stream order
+// into the first exception the reference would have raised (SURVEY.md Appendix A "ordering").
+//
+// Output placement: the frame format has no per-block decompressed size.  Blocks are placed
+// optimistically at frame_base + i * block_max (true for every encoder that fills its blocks);
+// the last block of a frame that is followed by another frame of the same stream is sized first
+// by K5.  A stream that violates the assumption (short interior block, match into the previous
+// block of an "independent" frame) is decoded again as one chain with exact running placement.
+#include <algorithm>
+#include <memory>
+
+#include "common.hpp"
+
+namespace lz4ada {
+
+struct FramePlan {
+	Format format = Format::TBD;
+	bool independent = true;
+	bool has_cchk = false;     // FLG bit 2
+	bool cchk_seen = false;    // the 4 checksum bytes were present in the stream
+	uint32_t cchk_declared = 0;
+	bool has_csize = false;
+	uint64_t csize = 0;
+	bool ended = false;        // end mark processed
+	uint32_t first_block = 0, n_blocks = 0;
+	uint32_t block_max = 0;
+	uint64_t dst_off = 0;      // frame base in the batch output
+	bool chained = false;      // decoded by K4
+	uint32_t hash_slot = 0xffffffffu;
+};
+
+struct ItemPlan {
+	uint64_t src_off = 0, src_len = 0, dst_off = 0, dst_cap = 0;
+	bool user_placed = false;
+	uint32_t first_frame = 0, n_frames = 0;   // data frames (legacy / modern)
+	uint32_t frames_seen = 0;                 // including skippable
+	uint32_t first_block = 0, n_blocks = 0;
+	Raised host_error;
+	int eof = LZ4ADA_EOF_NO;
+	bool slow = false;
+	// outcome of the last run
+	Raised error;
+	uint64_t out_len = 0;
+};
+
+class PlanEngine : public BlockEngine {
+public:
+	std::vector<FramePlan> *frames = nullptr;
+	std::vector<lz4b200_blk_desc> *descs = nullptr;
+	ItemPlan *item = nullptr;
+	uint64_t call_pos = 0;   // stream offset of the input handed to the current update call
+	int cur = -1;
+
+	Raised new_frame(Walker &) override
+	{
+		cur = -1;
+		return ok();
+	}
+	void frame_started(Walker &w) override
+	{
+		item->frames_seen++;
+		if (w.m.format != Format::Legacy && w.m.format != Format::Modern) return;
+		FramePlan f;
+		f.format = w.m.format;
+		f.independent = w.m.block_independent;
+		f.has_cchk = w.m.content_checksum_length != 0;
+		f.has_csize = w.m.has_content_size;
+		f.csize = w.m.has_content_size ? w.m.size_remaining : 0;
+		f.block_max = uint32_t(w.m.frame_block_max);
+		f.first_block = uint32_t(descs->size());
+		cur = int(frames->size());
+		frames->push_back(f);
+		item->n_frames++;
+	}
+	Raised block(Walker &w, const uint8_t *, int blk_len, uint8_t *, int, int &of, int &ol) override
+	{
+		of = 1;
+		ol = 0;
+		if (cur < 0) return err_assertion("block outside of a frame");
+		const int raw_len = blk_len - w.m.block_checksum_length;
+		lz4b200_blk_desc d;
+		memset(&d, 0, sizeof d);
+		d.src_off = item->src_off + call_pos + uint64_t(w.block_end_consumed) - uint64_t(blk_len);
+		d.src_len = uint32_t(raw_len);
+		d.flags = (w.m.is_compressed ? 0u : LZ4B200_BLK_STORED) |
+			  (w.m.block_checksum_length ? LZ4B200_BLK_HAS_CHECKSUM : 0u);
+		descs->push_back(d);
+		(*frames)[size_t(cur)].n_blocks++;
+		item->n_blocks++;
+		return ok();
+	}
+	Raised content_checksum(Walker &, uint32_t declared) override
+	{
+		if (cur >= 0) {
+			(*frames)[size_t(cur)].cchk_seen = true;
+			(*frames)[size_t(cur)].cchk_declared = declared;
+		}
+		return ok();   // compared after the device run
+	}
+	Raised frame_ended(Walker &) override
+	{
+		if (cur >= 0) (*frames)[size_t(cur)].ended = true;
+		return ok();   // content-size-left is checked after the device run
+	}
+};
+
+static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace lz4ada
+
+using namespace lz4ada;
+
+struct lz4ada_batch {
+	lz4b200_ctx *ctx = nullptr;
+	int reservation = LZ4ADA_FOR_ALL;
+	uint64_t src_bytes = 0;
+	std::vector<ItemPlan> items;
+	std::vector<FramePlan> frames;
+	std::vector<lz4b200_blk_desc> descs;
+	std::vector<lz4b200_chain> chains;
+	std::vector<lz4b200_frame_blocks> hash_frames;   // frames whose content checksum K3 computes
+	std::vector<uint32_t> presize;                   // blocks K5 sizes before placement
+	std::vector<uint32_t> sized;                     // their sizes once K5 has run
+	bool have_sized = false;
+	uint64_t out_bytes = 0;
+	bool placed = false;
+	bool tables_uploaded = false;
+	// device tables
+	lz4b200_blk_desc *d_desc = nullptr;
+	lz4b200_blk_status *d_status = nullptr;
+	lz4b200_chain *d_chains = nullptr;
+	lz4b200_frame_blocks *d_hash_frames = nullptr;
+	uint32_t *d_digest = nullptr;   // [n_hash] digests then [n_hash] valid flags
+	size_t cap_chains = 0;
+	// pinned host mirrors
+	lz4b200_blk_status *h_status = nullptr;
+	uint32_t *h_digest = nullptr;
+	// traffic of the last run
+	uint64_t t_comp = 0, t_out = 0, t_reread = 0;
+	std::string device_error;
+
+	~lz4ada_batch()
+	{
+		if (!ctx) return;   // never reached the device
+		lz4b200_sync(ctx);
+		if (d_desc) lz4b200_free(ctx, d_desc);
+		if (d_status) lz4b200_free(ctx, d_status);
+		if (d_chains) lz4b200_free(ctx, d_chains);
+		if (d_hash_frames) lz4b200_free(ctx, d_hash_frames);
+		if (d_digest) lz4b200_free(ctx, d_digest);
+		if (h_status) lz4b200_free_host(ctx, h_status);
+		if (h_digest) lz4b200_free_host(ctx, h_digest);
+	}
+};
+
+namespace {
+
+// Optimistic placement.  `sized` = out_len of pre-sized blocks (indexed like b->presize) or null.
+void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
+{
+	std::vector<int64_t> known(b->descs.size(), -1);
+	if (sized_len)
+		for (size_t i = 0; i < b->presize.size(); i++) known[b->presize[i]] = (*sized_len)[i];
+	b->chains.clear();
+	b->hash_frames.clear();
+	uint64_t cursor = 0;
+	for (ItemPlan &it : b->items) {
+		it.slow = false;
+		uint64_t upper = 0;
+		for (uint32_t f = 0; f < it.n_frames; f++) {
+			const FramePlan &fp = b->frames[it.first_frame + f];
+			upper += uint64_t(fp.n_blocks) * fp.block_max;
+		}
+		if (!it.user_placed) {
+			it.dst_off = align_up(cursor, 256);
+			it.dst_cap = upper;
+		}
+		const uint64_t item_end = it.dst_off + it.dst_cap;
+		uint64_t pos = it.dst_off;
+		for (uint32_t f = 0; f < it.n_frames; f++) {
+			FramePlan &fp = b->frames[it.first_frame + f];
+			fp.dst_off = pos;
+			fp.chained = !fp.independent && fp.n_blocks > 1;
+			fp.hash_slot = 0xffffffffu;
+			for (uint32_t i = 0; i < fp.n_blocks; i++) {
+				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
+				d.dst_off = fp.dst_off + uint64_t(i) * fp.block_max;
+				const uint64_t room = d.dst_off < item_end ? item_end - d.dst_off : 0;
+				d.dst_cap = uint32_t(std::min<uint64_t>(fp.block_max, room));
+				if (room < fp.block_max && i + 1 < fp.n_blocks) it.slow = true;   // tight user buffer
+				const uint64_t hist = uint64_t(i) * fp.block_max;
+				d.hist_avail = hist > 0xfffffffeull ? 0xffffffffu : uint32_t(hist);
+				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME);
+				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
+				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
+			}
+			if (fp.chained) {
+				lz4b200_chain c;
+				c.first_block = fp.first_block;
+				c.n_blocks = fp.n_blocks;
+				c.dst_off = fp.dst_off;
+				c.dst_cap = fp.dst_off < item_end ? std::min<uint64_t>(uint64_t(fp.n_blocks) * fp.block_max,
+										      item_end - fp.dst_off)
+								  : 0;
+				b->chains.push_back(c);
+			}
+			if (fp.has_cchk && fp.cchk_seen) {
+				fp.hash_slot = uint32_t(b->hash_frames.size());
+				lz4b200_frame_blocks hb;
+				hb.first_block = fp.first_block;
+				hb.n_blocks = fp.n_blocks;
+				b->hash_frames.push_back(hb);
+			}
+			// where the next frame of this stream starts: interior blocks full, last block sized by K5
+			uint64_t fsize = 0;
+			if (fp.n_blocks) {
+				const uint32_t last = fp.first_block + fp.n_blocks - 1;
+				const int64_t k = known[last];
+				fsize = uint64_t(fp.n_blocks - 1) * fp.block_max + (k >= 0 ? uint64_t(k) : fp.block_max);
+			}
+			pos += fsize;
+		}
+		if (!it.user_placed) cursor = it.dst_off + it.dst_cap;
+		else cursor = std::max(cursor, item_end);
+	}
+	b->out_bytes = cursor;
+	b->placed = true;
+}
+
+Raised device_fail(lz4ada_batch *b)
+{
+	b->device_error = lz4b200_last_error(b->ctx);
+	return err_device(b->device_error.c_str());
+}
+
+// Fold the statuses of one stream in stream order.  exact = the stream was decoded as one chain
+// (placement is exact by construction; frame bases are recomputed here).
+// digest_of(frame) must deliver (valid, value).
+template <class DigestFn>
+void fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
+{
+	if (!exact && it.slow) return;   // placement already known to be unusable (tight caller buffer)
+	it.error = Raised();
+	it.out_len = 0;
+	bool slow = false;
+	uint64_t pos = it.dst_off;
+	for (uint32_t f = 0; f < it.n_frames && !it.error && !slow; f++) {
+		FramePlan &fp = b->frames[it.first_frame + f];
+		if (exact) fp.dst_off = pos;
+		else if (fp.dst_off != pos) { slow = true; break; }
+		uint64_t fpos = 0;
+		uint64_t remaining = fp.csize;
+		for (uint32_t i = 0; i < fp.n_blocks; i++) {
+			const uint32_t bi = fp.first_block + i;
+			const lz4b200_blk_status &st = b->h_status[bi];
+			const lz4b200_blk_desc &d = b->descs[bi];
+			if (st.code == LZ4B200_ST_NEEDS_HISTORY || st.code == LZ4B200_ST_NOT_RUN) { slow = true; break; }
+			if (!exact && !fp.chained && d.dst_off != fp.dst_off + fpos) { slow = true; break; }
+			if (fp.has_csize && st.code != LZ4B200_ST_BLOCK_CHECKSUM) {
+				const uint64_t produced = st.code == LZ4B200_ST_OK ? st.out_len : st.err_pos;
+				if (remaining < produced) { it.error = err_content_size_exceeded(); break; }
+			}
+			if (st.code != LZ4B200_ST_OK) {
+				if (st.code == LZ4B200_ST_OUTPUT_OVERFLOW && !exact && d.dst_cap < fp.block_max) { slow = true; break; }
+				it.error = status_to_raised(st, int(std::min<uint64_t>(d.dst_cap, 0x7fffffff)));
+				break;
+			}
+			remaining -= st.out_len;
+			fpos += st.out_len;
+		}
+		if (it.error || slow) break;
+		pos += fpos;
+		it.out_len += fpos;
+		if (fp.has_cchk && fp.cchk_seen) {
+			uint32_t value = 0;
+			if (!digest_of(fp, value)) { slow = true; break; }
+			if (value != fp.cchk_declared) { it.error = err_content_checksum(value, fp.cchk_declared); break; }
+		}
+		if (fp.ended && fp.has_csize && remaining != 0) { it.error = err_content_size_left(remaining); break; }
+	}
+	if (slow) {
+		it.slow = true;
+		return;
+	}
+	if (!it.error) it.error = it.host_error;
+}
+
+// Decode the flagged streams again, each as one chain with exact running placement.
+Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
+{
+	std::vector<lz4b200_chain> chains;
+	for (ItemPlan &it : b->items) {
+		if (!it.slow || it.n_blocks == 0) continue;
+		for (uint32_t f = 0; f < it.n_frames; f++) {
+			FramePlan &fp = b->frames[it.first_frame + f];
+			for (uint32_t i = 0; i < fp.n_blocks; i++) {
+				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
+				d.flags |= LZ4B200_BLK_CHAINED;
+				d.dst_cap = fp.block_max;
+			}
+		}
+		lz4b200_chain c;
+		c.first_block = it.first_block;
+		c.n_blocks = it.n_blocks;
+		c.dst_off = it.dst_off;
+		c.dst_cap = it.dst_cap;
+		chains.push_back(c);
+		if (lz4b200_h2d(b->ctx, b->d_desc + it.first_block, b->descs.data() + it.first_block,
+				sizeof(lz4b200_blk_desc) * it.n_blocks) != LZ4B200_OK)
+			return device_fail(b);
+	}
+	if (chains.empty()) return ok();
+	if (chains.size() > b->cap_chains) {
+		if (b->d_chains) lz4b200_free(b->ctx, b->d_chains);
+		b->d_chains = nullptr;
+		b->cap_chains = chains.size();
+		if (lz4b200_alloc(b->ctx, sizeof(lz4b200_chain) * b->cap_chains, reinterpret_cast<void **>(&b->d_chains)) != LZ4B200_OK)
+			return device_fail(b);
+	}
+	if (lz4b200_h2d(b->ctx, b->d_chains, chains.data(), sizeof(lz4b200_chain) * chains.size()) != LZ4B200_OK ||
+	    lz4b200_decode_linked(b->ctx, src_dev, dst_dev, uint32_t(chains.size()), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK ||
+	    lz4b200_d2h(b->ctx, b->h_status, b->d_status, sizeof(lz4b200_blk_status) * b->descs.size()) != LZ4B200_OK ||
+	    lz4b200_sync(b->ctx) != LZ4B200_OK)
+		return device_fail(b);
+	// content checksums of the re-placed frames: spans are known only now
+	std::vector<lz4b200_hash_span> spans;
+	std::vector<FramePlan *> span_frames;
+	for (ItemPlan &it : b->items) {
+		if (!it.slow) continue;
+		uint64_t pos = it.dst_off;
+		for (uint32_t f = 0; f < it.n_frames; f++) {
+			FramePlan &fp = b->frames[it.first_frame + f];
+			uint64_t len = 0;
+			bool okay = true;
+			for (uint32_t i = 0; i < fp.n_blocks; i++) {
+				const lz4b200_blk_status &st = b->h_status[fp.first_block + i];
+				if (st.code != LZ4B200_ST_OK) { okay = false; break; }
+				len += st.out_len;
+			}
+			if (!okay) break;
+			if (fp.has_cchk && fp.cchk_seen) {
+				lz4b200_hash_span s;
+				s.off = pos;
+				s.len = len;
+				spans.push_back(s);
+				span_frames.push_back(&fp);
+			}
+			pos += len;
+		}
+	}
+	std::vector<uint32_t> values(spans.size());
+	if (!spans.empty()) {
+		lz4b200_hash_span *d_spans = nullptr;
+		uint32_t *d_out = nullptr;
+		if (lz4b200_alloc(b->ctx, sizeof(lz4b200_hash_span) * spans.size(), reinterpret_cast<void **>(&d_spans)) != LZ4B200_OK ||
+		    lz4b200_alloc(b->ctx, 4 * spans.size(), reinterpret_cast<void **>(&d_out)) != LZ4B200_OK)
+			return device_fail(b);
+		bool bad = lz4b200_h2d(b->ctx, d_spans, spans.data(), sizeof(lz4b200_hash_span) * spans.size()) != LZ4B200_OK ||
+			   lz4b200_xxh32_spans(b->ctx, dst_dev, uint32_t(spans.size()), d_spans, d_out) != LZ4B200_OK ||
+			   lz4b200_d2h(b->ctx, values.data(), d_out, 4 * spans.size()) != LZ4B200_OK ||
+			   lz4b200_sync(b->ctx) != LZ4B200_OK;
+		lz4b200_free(b->ctx, d_spans);
+		lz4b200_free(b->ctx, d_out);
+		if (bad) return device_fail(b);
+	}
+	for (ItemPlan &it : b->items) {
+		if (!it.slow) continue;
+		fold_item(b, it, true, [&](const FramePlan &fp, uint32_t &value) {
+			for (size_t k = 0; k < span_frames.size(); k++)
+				if (span_frames[k] == &fp) { value = values[k]; return true; }
+			return false;
+		});
+		if (it.slow && !it.error) {   // cannot happen: the chain path has no soft failures
+			it.error = err_device("chain decode reported an unexpected soft status");
+		}
+	}
+	return ok();
+}
+
+}  // namespace
+
+extern "C" {
+
+int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes, uint32_t n_items,
+		      const lz4ada_batch_item *items, int reservation, lz4ada_batch **out)
+{
+	if (!out || (!items && n_items) || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SZ_8_MIB)
+		return LZ4ADA_ASSERTION_ERROR;
+	*out = nullptr;
+	// planning is pure host work; the device context is only needed from upload on
+	std::unique_ptr<lz4ada_batch> b(new lz4ada_batch());
+	b->ctx = ctx;
+	b->reservation = reservation;
+	b->src_bytes = src_bytes;
+	b->items.resize(n_items);
+	PlanEngine engine;
+	engine.frames = &b->frames;
+	engine.descs = &b->descs;
+	const int in_last = block_size_of(reservation) + 4 + kBlockSizeBytes - 1;   // as Init, lib/lz4ada.adb:60
+	for (uint32_t k = 0; k < n_items; k++) {
+		ItemPlan &it = b->items[k];
+		it.src_off = items[k].src_off;
+		it.src_len = items[k].src_len;
+		it.dst_off = items[k].dst_off;
+		it.dst_cap = items[k].dst_cap;
+		it.user_placed = items[k].dst_cap != 0;
+		it.first_frame = uint32_t(b->frames.size());
+		it.first_block = uint32_t(b->descs.size());
+		if (it.src_off > src_bytes || it.src_len > src_bytes - it.src_off) return LZ4ADA_ASSERTION_ERROR;
+		Meta m;
+		m.reservation = reservation;
+		Walker w(m, in_last, &engine);
+		engine.item = &it;
+		engine.cur = -1;
+		const uint8_t *s = src_host + it.src_off;
+		uint64_t pos = 0;
+		int idle = 0;
+		while (pos < it.src_len) {
+			const uint64_t left = it.src_len - pos;
+			const int window = int(std::min<uint64_t>(left, 0x40000000ull));
+			int consumed = 0, of = 1, ol = 0;
+			engine.call_pos = pos;
+			Raised r = w.update(s + pos, window, consumed, nullptr, 0, of, ol);
+			if (r) {
+				it.host_error = r;
+				break;
+			}
+			pos += uint64_t(consumed);
+			if (consumed == 0 && ++idle > 2) {
+				it.host_error = err_assertion("No more data accepted but no exception signalled.");
+				break;
+			}
+			if (consumed) idle = 0;
+		}
+		it.eof = w.is_end_of_frame();
+	}
+	// blocks whose size decides where the next frame of the same stream starts
+	for (ItemPlan &it : b->items)
+		for (uint32_t f = 0; f + 1 < it.n_frames; f++) {
+			const FramePlan &fp = b->frames[it.first_frame + f];
+			if (fp.n_blocks) b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+		}
+	if (b->presize.empty()) place(b.get(), nullptr);
+	else {
+		// upper bound so that callers can allocate before the sizes are known
+		place(b.get(), nullptr);
+		b->placed = false;
+	}
+	*out = b.release();
+	return LZ4ADA_OK;
+}
+
+int lz4ada_batch_block_desc(const lz4ada_batch *b, uint64_t index, lz4b200_blk_desc *out)
+{
+	if (!b || !out || index >= b->descs.size()) return LZ4ADA_ASSERTION_ERROR;
+	*out = b->descs[index];
+	return LZ4ADA_OK;
+}
+
+int lz4ada_batch_host_outcome(const lz4ada_batch *b, uint32_t item, int *exception, int *end_of_frame,
+			      uint32_t *n_frames, uint32_t *n_blocks, char *message, size_t message_cap)
+{
+	if (!b || item >= b->items.size()) return LZ4ADA_ASSERTION_ERROR;
+	const ItemPlan &it = b->items[item];
+	if (exception) *exception = it.host_error.kind;
+	if (end_of_frame) *end_of_frame = it.eof;
+	if (n_frames) *n_frames = it.frames_seen;
+	if (n_blocks) *n_blocks = it.n_blocks;
+	if (message && message_cap) {
+		const size_t n = std::min(it.host_error.text.size(), message_cap - 1);
+		memcpy(message, it.host_error.text.data(), n);
+		message[n] = 0;
+	}
+	return LZ4ADA_OK;
+}
+
+uint64_t lz4ada_batch_output_bytes(const lz4ada_batch *b) { return b ? b->out_bytes : 0; }
+uint64_t lz4ada_batch_block_count(const lz4ada_batch *b) { return b ? b->descs.size() : 0; }
+
+void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read, uint64_t *decompressed_written,
+			  uint64_t *checksum_reread)
+{
+	if (compressed_read) *compressed_read = b ? b->t_comp : 0;
+	if (decompressed_written) *decompressed_written = b ? b->t_out : 0;
+	if (checksum_reread) *checksum_reread = b ? b->t_reread : 0;
+}
+
+int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_dev)
+{
+	if (!b) return LZ4ADA_ASSERTION_ERROR;
+	if (!b->ctx) {
+		Raised why;
+		b->ctx = default_context(&why);
+		if (!b->ctx) return LZ4ADA_DEVICE_ERROR;
+	}
+	lz4b200_ctx *ctx = b->ctx;
+	const size_t nb = b->descs.size();
+	if (src_host && src_dev && lz4b200_h2d(ctx, src_dev, src_host, b->src_bytes) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+	if (!b->d_desc && nb) {
+		if (lz4b200_alloc(ctx, sizeof(lz4b200_blk_desc) * nb, reinterpret_cast<void **>(&b->d_desc)) != LZ4B200_OK ||
+		    lz4b200_alloc(ctx, sizeof(lz4b200_blk_status) * nb, reinterpret_cast<void **>(&b->d_status)) != LZ4B200_OK ||
+		    lz4b200_alloc_host(ctx, sizeof(lz4b200_blk_status) * nb, reinterpret_cast<void **>(&b->h_status)) != LZ4B200_OK)
+			return LZ4ADA_DEVICE_ERROR;
+	}
+	if (!b->placed && nb) {
+		// K5 over the blocks that decide frame bases (needs the compressed bytes on the device)
+		std::vector<lz4b200_blk_desc> pd(b->presize.size());
+		for (size_t i = 0; i < pd.size(); i++) pd[i] = b->descs[b->presize[i]];
+		lz4b200_blk_desc *d_pd = nullptr;
+		lz4b200_blk_status *d_ps = nullptr;
+		std::vector<lz4b200_blk_status> ps(pd.size());
+		if (lz4b200_alloc(ctx, sizeof(lz4b200_blk_desc) * pd.size(), reinterpret_cast<void **>(&d_pd)) != LZ4B200_OK ||
+		    lz4b200_alloc(ctx, sizeof(lz4b200_blk_status) * pd.size(), reinterpret_cast<void **>(&d_ps)) != LZ4B200_OK)
+			return LZ4ADA_DEVICE_ERROR;
+		const bool bad = lz4b200_h2d(ctx, d_pd, pd.data(), sizeof(lz4b200_blk_desc) * pd.size()) != LZ4B200_OK ||
+				 lz4b200_size_blocks(ctx, src_dev, uint32_t(pd.size()), d_pd, d_ps) != LZ4B200_OK ||
+				 lz4b200_d2h(ctx, ps.data(), d_ps, sizeof(lz4b200_blk_status) * pd.size()) != LZ4B200_OK ||
+				 lz4b200_sync(ctx) != LZ4B200_OK;
+		lz4b200_free(ctx, d_pd);
+		lz4b200_free(ctx, d_ps);
+		if (bad) return LZ4ADA_DEVICE_ERROR;
+		std::vector<uint32_t> &sized = b->sized;
+		sized.assign(pd.size(), 0);
+		b->have_sized = true;
+		for (size_t i = 0; i < pd.size(); i++) {
+			const FramePlan *owner = nullptr;
+			for (const FramePlan &fp : b->frames)
+				if (fp.n_blocks && fp.first_block + fp.n_blocks - 1 == b->presize[i]) { owner = &fp; break; }
+			const uint32_t bm = owner ? owner->block_max : 0xffffffffu;
+			sized[i] = std::min(ps[i].out_len, bm);   // a longer block fails in K1 anyway
+		}
+		const uint64_t upper = b->out_bytes;
+		place(b, &sized);
+		b->out_bytes = std::max(b->out_bytes, upper);   // never shrink what the caller allocated from
+		b->tables_uploaded = false;
+	}
+	if (!b->tables_uploaded && nb) {
+		const size_t nh = b->hash_frames.size(), nc = b->chains.size();
+		if (nc > b->cap_chains) {
+			if (b->d_chains) lz4b200_free(ctx, b->d_chains);
+			b->cap_chains = nc;
+			if (lz4b200_alloc(ctx, sizeof(lz4b200_chain) * nc, reinterpret_cast<void **>(&b->d_chains)) != LZ4B200_OK)
+				return LZ4ADA_DEVICE_ERROR;
+		}
+		if (nh && !b->d_hash_frames) {
+			if (lz4b200_alloc(ctx, sizeof(lz4b200_frame_blocks) * nh, reinterpret_cast<void **>(&b->d_hash_frames)) != LZ4B200_OK ||
+			    lz4b200_alloc(ctx, 8 * nh, reinterpret_cast<void **>(&b->d_digest)) != LZ4B200_OK ||
+			    lz4b200_alloc_host(ctx, 8 * nh, reinterpret_cast<void **>(&b->h_digest)) != LZ4B200_OK)
+				return LZ4ADA_DEVICE_ERROR;
+		}
+		if (lz4b200_h2d(ctx, b->d_desc, b->descs.data(), sizeof(lz4b200_blk_desc) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		if (nc && lz4b200_h2d(ctx, b->d_chains, b->chains.data(), sizeof(lz4b200_chain) * nc) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		if (nh && lz4b200_h2d(ctx, b->d_hash_frames, b->hash_frames.data(), sizeof(lz4b200_frame_blocks) * nh) != LZ4B200_OK)
+			return LZ4ADA_DEVICE_ERROR;
+		if (lz4b200_sync(ctx) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		b->tables_uploaded = true;
+	}
+	return LZ4ADA_OK;
+}
+
+int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
+{
+	if (!b || !b->ctx) return LZ4ADA_ASSERTION_ERROR;
+	lz4b200_ctx *ctx = b->ctx;
+	const size_t nb = b->descs.size(), nh = b->hash_frames.size(), nc = b->chains.size();
+	if (nb) {
+		if (!b->tables_uploaded) return LZ4ADA_ASSERTION_ERROR;
+		bool any_slow_before = false;
+		for (ItemPlan &it : b->items)
+			if (it.slow) any_slow_before = true;
+		if (any_slow_before) {
+			// a previous run re-placed some streams; restore the optimistic tables
+			place(b, b->have_sized ? &b->sized : nullptr);
+			if (lz4b200_h2d(ctx, b->d_desc, b->descs.data(), sizeof(lz4b200_blk_desc) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		}
+		if (lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(nb), b->d_desc, b->d_status) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		if (nc && lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(nc), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK)
+			return LZ4ADA_DEVICE_ERROR;
+		if (nh && lz4b200_xxh32_frames(ctx, dst_dev, uint32_t(nh), b->d_hash_frames, b->d_desc, b->d_status, b->d_digest,
+						b->d_digest + nh) != LZ4B200_OK)
+			return LZ4ADA_DEVICE_ERROR;
+		if (lz4b200_d2h(ctx, b->h_status, b->d_status, sizeof(lz4b200_blk_status) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		if (nh && lz4b200_d2h(ctx, b->h_digest, b->d_digest, 8 * nh) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		if (lz4b200_sync(ctx) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+	}
+	bool any_slow = false;
+	for (ItemPlan &it : b->items) {
+		fold_item(b, it, false, [&](const FramePlan &fp, uint32_t &value) {
+			if (fp.hash_slot == 0xffffffffu || !b->h_digest[nh + fp.hash_slot]) return false;
+			value = b->h_digest[fp.hash_slot];
+			return true;
+		});
+		if (it.slow) any_slow = true;
+	}
+	if (any_slow) {
+		Raised r = run_slow_items(b, src_dev, dst_dev);
+		if (r) return LZ4ADA_DEVICE_ERROR;
+	}
+	// traffic of this run: C + D + D for checksummed frames
+	b->t_comp = b->t_out = b->t_reread = 0;
+	for (const FramePlan &fp : b->frames) {
+		uint64_t out = 0;
+		for (uint32_t i = 0; i < fp.n_blocks; i++) {
+			const lz4b200_blk_desc &d = b->descs[fp.first_block + i];
+			b->t_comp += uint64_t(d.src_len) + 4 + ((d.flags & LZ4B200_BLK_HAS_CHECKSUM) ? 4 : 0);
+			if (b->h_status && b->h_status[fp.first_block + i].code == LZ4B200_ST_OK) out += b->h_status[fp.first_block + i].out_len;
+		}
+		b->t_out += out;
+		if (fp.has_cchk && fp.cchk_seen) b->t_reread += out;
+	}
+	return LZ4ADA_OK;
+}
+
+int lz4ada_batch_results(const lz4ada_batch *b, lz4ada_batch_result *results)
+{
+	if (!b || !results) return LZ4ADA_ASSERTION_ERROR;
+	for (size_t k = 0; k < b->items.size(); k++) {
+		const ItemPlan &it = b->items[k];
+		results[k].exception = it.error.kind;
+		results[k].end_of_frame = it.eof;
+		results[k].n_frames = it.frames_seen;
+		results[k].n_blocks = it.n_blocks;
+		results[k].dst_off = it.dst_off;
+		results[k].out_len = it.out_len;
+	}
+	return LZ4ADA_OK;
+}
+
+const char *lz4ada_batch_message(const lz4ada_batch *b, uint32_t item)
+{
+	if (!b || item >= b->items.size()) return "";
+	return b->items[item].error.text.c_str();
+}
+
+void lz4ada_batch_free(lz4ada_batch *b) { delete b; }
+
+int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes, uint8_t *dst_host,
+			    uint64_t dst_bytes, uint32_t n_items, lz4ada_batch_item *items, int reservation,
+			    lz4ada_batch_result *results, char *messages, size_t message_stride)
+{
+	lz4ada_batch *b = nullptr;
+	int rc = lz4ada_batch_plan(ctx, src_host, src_bytes, n_items, items, reservation, &b);
+	if (rc != LZ4ADA_OK) return rc;
+	std::unique_ptr<lz4ada_batch> guard(b);
+	if (!b->ctx) {
+		Raised why;
+		b->ctx = default_context(&why);
+		if (!b->ctx) return LZ4ADA_DEVICE_ERROR;
+	}
+	ctx = b->ctx;
+	uint8_t *d_src = nullptr, *d_dst = nullptr;
+	if (lz4b200_alloc(ctx, src_bytes + 64, reinterpret_cast<void **>(&d_src)) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+	rc = lz4ada_batch_upload(b, src_host, d_src);
+	const uint64_t need = lz4ada_batch_output_bytes(b);
+	if (rc == LZ4ADA_OK && need > dst_bytes) rc = LZ4ADA_ASSERTION_ERROR;
+	if (rc == LZ4ADA_OK && lz4b200_alloc(ctx, need + 64, reinterpret_cast<void **>(&d_dst)) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+	if (rc == LZ4ADA_OK) rc = lz4ada_batch_run(b, d_src, d_dst);
+	if (rc == LZ4ADA_OK) {
+		// bring back exactly what each stream produced
+		for (const ItemPlan &it : b->items)
+			if (it.out_len && lz4b200_d2h(ctx, dst_host + it.dst_off, d_dst + it.dst_off, it.out_len) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+		if (lz4b200_sync(ctx) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+	}
+	if (rc == LZ4ADA_OK && results) lz4ada_batch_results(b, results);
+	if (rc == LZ4ADA_OK && messages && message_stride)
+		for (uint32_t k = 0; k < n_items; k++) {
+			const std::string &t = b->items[k].error.text;
+			const size_t n = std::min(t.size(), message_stride - 1);
+			memcpy(messages + size_t(k) * message_stride, t.data(), n);
+			messages[size_t(k) * message_stride + n] = 0;
+		}
+	if (rc == LZ4ADA_OK)
+		for (uint32_t k = 0; k < n_items; k++) {
+			items[k].dst_off = b->items[k].dst_off;
+			items[k].dst_cap = b->items[k].dst_cap;
+		}
+	if (d_src) lz4b200_free(ctx, d_src);
+	if (d_dst) lz4b200_free(ctx, d_dst);
+	return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// decompressor.cpp -- the LZ4Ada package API over the device shim: Init, Init_With_Header,
+// Init_For_Block, Update, Is_End_Of_Frame, To_Hex, XXHash32 (lib/lz4ada.ads:50-344).
+//
+// Update keeps the reference's contract: the caller's Buffer receives one block per call at the
+// same ring position the reference would use (Output_First / Output_Last), and the same
+// exception fires at the same byte.  What differs is where the work happens: a complete block
+// goes H2D, is decoded by one warp against a device-resident 64 KiB history window, and the
+// produced bytes come back D2H (lz4b200_stream_block).  There is no host-side LZ4 decoder.
+#include <mutex>
+
+#include "common.hpp"
+
+namespace lz4ada {
+
+// ---- process-wide default device context -------------------------------------------------
+static std::mutex g_ctx_mutex;
+static lz4b200_ctx *g_ctx = nullptr;
+static bool g_ctx_owned = false;
+
+lz4b200_ctx *default_context(Raised *why)
+{
+	std::lock_guard<std::mutex> lock(g_ctx_mutex);
+	if (!g_ctx) {
+		lz4b200_ctx *c = nullptr;
+		if (lz4b200_create(0, nullptr, &c) != LZ4B200_OK) {
+			if (why)
+				*why = err_device("no CUDA device / context available -- this library has no CPU "
+						  "decode path");
+			return nullptr;
+		}
+		g_ctx = c;
+		g_ctx_owned = true;
+	}
+	return g_ctx;
+}
+
+// ---- streaming engine: one block at a time on the device ---------------------------------
+class DeviceStreamEngine : public BlockEngine {
+public:
+	explicit DeviceStreamEngine(int stream_block_max) : max_block_(uint32_t(stream_block_max)) {}
+	~DeviceStreamEngine() override
+	{
+		if (stream_) lz4b200_stream_destroy(stream_);
+	}
+
+	Raised new_frame(Walker &) override   // Reset_Outer_For_Next_Frame, lib/lz4ada.adb:451-461
+	{
+		output_pos_ = 0;
+		if (stream_ && lz4b200_stream_reset(stream_) != LZ4B200_OK) return device_failure();
+		return ok();
+	}
+
+	Raised block(Walker &w, const uint8_t *blk, int blk_len, uint8_t *buffer, int buffer_len, int &of,
+		     int &ol) override   // Decode_Full_Block_With_Trailer, :661-696
+	{
+		if (Raised r = ensure_stream()) return r;
+		const int raw_len = blk_len - w.m.block_checksum_length;
+		if (output_pos_ >= kHistorySize) output_pos_ = 0;   // ring cursor, :678-680
+		int64_t cap = int64_t(buffer_len) - output_pos_;
+		if (cap < 0) cap = 0;
+		if (cap > int64_t(max_block_)) cap = max_block_;
+		uint32_t flags = 0;
+		if (!w.m.is_compressed) flags |= LZ4B200_BLK_STORED;
+		if (w.m.block_checksum_length) flags |= LZ4B200_BLK_HAS_CHECKSUM;
+		lz4b200_blk_status st;
+		memset(&st, 0, sizeof st);
+		if (lz4b200_stream_block(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
+					 buffer + output_pos_, uint32_t(cap), &st) != LZ4B200_OK)
+			return device_failure();
+		// Decrease_Data_Size_Remaining (:826-839) fires inside Write_Output, i.e. before any
+		// later check of the same block; the block checksum (:672-676) comes before everything.
+		if (w.m.has_content_size && st.code != LZ4B200_ST_BLOCK_CHECKSUM) {
+			const uint64_t produced = st.code == LZ4B200_ST_OK ? st.out_len : st.err_pos;
+			if (w.m.size_remaining < produced) return err_content_size_exceeded();
+		}
+		if (st.code != LZ4B200_ST_OK) return status_to_raised(st, buffer_len);
+		if (w.m.has_content_size) w.m.size_remaining -= st.out_len;
+		of = output_pos_;
+		ol = output_pos_ + int(st.out_len) - 1;
+		output_pos_ += int(st.out_len);
+		return ok();
+	}
+
+	Raised content_checksum(Walker &, uint32_t declared) override   // :493-511
+	{
+		if (Raised r = ensure_stream()) return r;
+		uint32_t computed = 0;
+		if (lz4b200_stream_digest(stream_, &computed) != LZ4B200_OK) return device_failure();
+		if (computed != declared) return err_content_checksum(computed, declared);
+		return ok();
+	}
+
+	Raised frame_ended(Walker &w) override   // Set_Frame_Has_Ended, :465-477
+	{
+		if (w.m.has_content_size && w.m.size_remaining != 0) return err_content_size_left(w.m.size_remaining);
+		return ok();
+	}
+
+private:
+	Raised ensure_stream()
+	{
+		if (stream_) return ok();
+		Raised why;
+		ctx_ = default_context(&why);
+		if (!ctx_) return why;
+		if (lz4b200_stream_create(ctx_, max_block_, &stream_) != LZ4B200_OK) return device_failure();
+		return ok();
+	}
+	Raised device_failure() { return err_device(ctx_ ? lz4b200_last_error(ctx_) : "no device context"); }
+
+	uint32_t max_block_;
+	lz4b200_ctx *ctx_ = nullptr;
+	lz4b200_stream *stream_ = nullptr;
+	int output_pos_ = 0;   // Output_Pos of the reference's ring
+};
+
+}  // namespace lz4ada
+
+using namespace lz4ada;
+
+struct lz4ada_decompressor {
+	DeviceStreamEngine engine;
+	Walker walker;
+	std::string message;
+	lz4ada_decompressor(const Meta &m, int in_last, int min_buffer_size)
+		: engine(min_buffer_size), walker(m, in_last, &engine)
+	{
+	}
+};
+
+static void copy_message(char *dst, size_t cap, const std::string &s)
+{
+	if (!dst || !cap) return;
+	const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+	memcpy(dst, s.data(), n);
+	dst[n] = 0;
+}
+
+extern "C" {
+
+int lz4ada_set_device_context(lz4b200_ctx *ctx)
+{
+	std::lock_guard<std::mutex> lock(g_ctx_mutex);
+	if (g_ctx && g_ctx_owned && g_ctx != ctx) lz4b200_destroy(g_ctx);
+	g_ctx = ctx;
+	g_ctx_owned = false;
+	return LZ4ADA_OK;
+}
+
+int lz4ada_init(int *min_buffer_size, int reservation, lz4ada_decompressor **out)   // lib/lz4ada.adb:48-63
+{
+	if (!min_buffer_size || !out || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SZ_8_MIB)
+		return LZ4ADA_ASSERTION_ERROR;
+	const int block_max = block_size_of(reservation);
+	*min_buffer_size = block_max + kHistorySize + 8;
+	Meta m;
+	m.reservation = reservation;
+	*out = new lz4ada_decompressor(m, block_max + 4 + kBlockSizeBytes - 1, *min_buffer_size);
+	return LZ4ADA_OK;
+}
+
+int lz4ada_init_with_header(const uint8_t *input, int input_len, int *num_consumed, int *min_buffer_size,
+			    int reservation, lz4ada_decompressor **out, char *message, size_t message_cap)
+{   // lib/lz4ada.adb:79-125
+	if (!num_consumed || !min_buffer_size || !out) return LZ4ADA_ASSERTION_ERROR;
+	*out = nullptr;
+	*num_consumed = 0;
+	Raised r;
+	if (!input || input_len < 7) {   // Pre => Input'Length >= 7, lib/lz4ada.ads:243
+		r = err_assertion("failed precondition from lz4ada.ads:243");
+		copy_message(message, message_cap, r.text);
+		return r.kind;
+	}
+	uint8_t header_buffer[20];
+	Meta mt;
+	mt.reservation = reservation == LZ4ADA_SINGLE_FRAME ? LZ4ADA_USE_FIRST : reservation;
+	int pos = 0;
+	while (mt.stage != HeaderStage::Complete) {
+		if (pos >= input_len) {
+			r = err_too_few_header_bytes(mt.size_remaining);
+			copy_message(message, message_cap, r.text);
+			return r.kind;
+		}
+		int inner = 0;
+		r = header_feed(mt, header_buffer, input + pos, input_len - pos, inner);
+		if (r) {
+			copy_message(message, message_cap, r.text);
+			return r.kind;
+		}
+		pos += inner;
+		*num_consumed += inner;
+	}
+	const int block_max = block_size_of(mt.reservation);
+	const int in_last = block_max + mt.block_checksum_length + kBlockSizeBytes - 1;
+	*min_buffer_size = block_max + kHistorySize + 8;
+	if (reservation == LZ4ADA_SINGLE_FRAME) mt.reservation = LZ4ADA_SINGLE_FRAME;
+	*out = new lz4ada_decompressor(mt, in_last, *min_buffer_size);
+	return LZ4ADA_OK;
+}
+
+int lz4ada_init_for_block(int *min_buffer_size, int compressed_length, int reservation,
+			  lz4ada_decompressor **out)   // lib/lz4ada.adb:127-147
+{
+	if (!min_buffer_size || !out || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SZ_8_MIB)
+		return LZ4ADA_ASSERTION_ERROR;
+	const int block_max = block_size_of(reservation);
+	*min_buffer_size = block_max + kHistorySize + 8;
+	Meta m;
+	m.format = Format::Block;
+	m.is_compressed = true;
+	m.stage = HeaderStage::Complete;
+	m.reservation = reservation;
+	lz4ada_decompressor *d = new lz4ada_decompressor(m, block_max - 1, *min_buffer_size);
+	d->walker.input_length = compressed_length;
+	*out = d;
+	return LZ4ADA_OK;
+}
+
+int lz4ada_update(lz4ada_decompressor *ctx, const uint8_t *input, int input_len, int *num_consumed,
+		  uint8_t *buffer, int buffer_len, int *output_first, int *output_last)
+{
+	if (!ctx || !num_consumed || !output_first || !output_last) return LZ4ADA_ASSERTION_ERROR;
+	ctx->message.clear();
+	Raised r = ctx->walker.update(input, input_len, *num_consumed, buffer, buffer_len, *output_first, *output_last);
+	if (r) ctx->message = r.text;
+	return r.kind;
+}
+
+int lz4ada_is_end_of_frame(const lz4ada_decompressor *ctx) { return ctx->walker.is_end_of_frame(); }
+
+const char *lz4ada_exception_message(const lz4ada_decompressor *ctx) { return ctx ? ctx->message.c_str() : ""; }
+
+void lz4ada_free(lz4ada_decompressor *ctx) { delete ctx; }
+
+void lz4ada_to_hex_u8(uint8_t num, char *out)   // lib/lz4ada.adb:363-368
+{
+	static const char tbl[] = "0123456789abcdef";
+	out[0] = tbl[num >> 4];
+	out[1] = tbl[num & 15];
+	out[2] = 0;
+}
+
+void lz4ada_to_hex_u32(uint32_t num, char *out)   // lib/lz4ada.adb:370-375
+{
+	for (int i = 0; i < 4; i++) lz4ada_to_hex_u8(uint8_t(num >> (24 - 8 * i)), out + 2 * i);
+}
+
+// XXHash32.Init ignores its Seed argument (lib/lz4ada.adb:925-930 calls Reset without it).
+void lz4ada_xxhash32_init(lz4ada_xxhash32 *h, uint32_t seed)
+{
+	(void)seed;
+	Xxh32Host::reset(h, 0);
+}
+void lz4ada_xxhash32_reset(lz4ada_xxhash32 *h, uint32_t seed) { Xxh32Host::reset(h, seed); }
+void lz4ada_xxhash32_update(lz4ada_xxhash32 *h, const uint8_t *input, size_t len) { Xxh32Host::update(h, input, len); }
+uint32_t lz4ada_xxhash32_final(const lz4ada_xxhash32 *h) { return Xxh32Host::final(h); }
+uint32_t lz4ada_xxhash32_hash(const uint8_t *input, size_t len) { return Xxh32Host::hash(input, len); }
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+// kernels.cuh -- sm_100a device code of the LZ4 block decoder (K1/K4), XXH32 chains (K3),
+// size pre-pass (K5).  No tensor cores: the path is byte/integer work bounded by HBM and by
+// instruction issue.
+//
+// Reference code replaced (behaviour, not structure): lib/lz4ada.adb:661-904 (block decode),
+// :923-1026 (XXHash32).  The reference decodes serially into a 64 KiB ring; here every block
+// writes a flat output range, so the three-phase history copy of :845-904 collapses into one
+// backwards reference into already-written output.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lz4b200.h"
+
+namespace lz4b200 {
+
+constexpr uint32_t FULL_MASK = 0xffffffffu;
+// lib/lz4ada.ads:324-328
+constexpr uint32_t PRIME_1 = 2654435761u;
+constexpr uint32_t PRIME_2 = 2246822519u;
+constexpr uint32_t PRIME_3 = 3266489917u;
+constexpr uint32_t PRIME_4 = 668265263u;
+constexpr uint32_t PRIME_5 = 374761393u;
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int s) { return __funnelshift_l(v, v, s); }
+
+// Rot_Mul, lib/lz4ada.adb:982-985
+__device__ __forceinline__ uint32_t xxh_round(uint32_t acc, uint32_t x)
+{
+	return rotl32(acc + x * PRIME_2, 13) * PRIME_1;
+}
+
+// Loads.  RO = the bytes are never written during this kernel (compressed input, or output of an
+// earlier launch): non-coherent path.  Otherwise a plain load, ordered by __syncwarp().
+template <bool RO> __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p)
+{
+	if (RO) return __ldg(p);
+	return *p;
+}
+template <bool RO> __device__ __forceinline__ uint32_t ld_u32(const uint32_t *p)
+{
+	if (RO) return __ldg(p);
+	return *p;
+}
+template <bool RO> __device__ __forceinline__ uint4 ld_u128(const uint4 *p)
+{
+	if (RO) return __ldg(p);
+	return *p;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// XXH32 by a quad (4 consecutive lanes): lane `sub` owns accumulator `sub` and consumes word
+// `sub` of every 16-byte stripe (XXHash32.Process, lib/lz4ada.adb:979-991).  The chain is serial
+// per quad, so a warp carries eight independent chains.  All 32 lanes must call this together
+// (quads without work pass n = 0).  Every lane of the quad returns the digest of [p, p + n).
+// ---------------------------------------------------------------------------------------------
+struct XxhState {            // streaming state, same fields as lib/lz4ada.ads:335-343
+	uint32_t acc[4];
+	uint8_t  buf[16];
+	uint32_t buf_size;
+	uint32_t pad;
+	uint64_t total_len;
+};
+
+__device__ __forceinline__ uint32_t xxh_init_acc(int sub)   // Reset, :932-940 with Seed = 0
+{
+	return sub == 0 ? PRIME_1 + PRIME_2 : sub == 1 ? PRIME_2 : sub == 2 ? 0u : 0u - PRIME_1;
+}
+
+template <bool RO, bool PREFETCH>
+__device__ __forceinline__ uint32_t quad_stripes(const uint8_t *p, uint64_t nstripes, uint32_t acc,
+						 int sub)
+{
+	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+	const uint32_t mis = static_cast<uint32_t>(a & 3);
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis) + sub;
+	constexpr uint64_t AHEAD = 4096 / 16;   // stripes of L2 prefetch distance
+	uint64_t s = 0;
+	if (mis == 0) {
+		for (; s + 8 <= nstripes; s += 8) {
+			uint32_t x[8];
+			if (PREFETCH && sub == 0 && s + AHEAD < nstripes) prefetch_l2(w + (s + AHEAD) * 4);
+#pragma unroll
+			for (int j = 0; j < 8; j++) x[j] = ld_u32<RO>(w + (s + j) * 4);
+#pragma unroll
+			for (int j = 0; j < 8; j++) acc = xxh_round(acc, x[j]);
+		}
+		for (; s < nstripes; s++) acc = xxh_round(acc, ld_u32<RO>(w + s * 4));
+	} else {
+		const uint32_t sh = mis * 8;
+		for (; s + 8 <= nstripes; s += 8) {
+			uint32_t lo[8], hi[8];
+			if (PREFETCH && sub == 0 && s + AHEAD < nstripes) prefetch_l2(w + (s + AHEAD) * 4);
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				lo[j] = ld_u32<RO>(w + (s + j) * 4);
+				hi[j] = ld_u32<RO>(w + (s + j) * 4 + 1);
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++) acc = xxh_round(acc, __funnelshift_r(lo[j], hi[j], sh));
+		}
+		for (; s < nstripes; s++)
+			acc = xxh_round(acc, __funnelshift_r(ld_u32<RO>(w + s * 4), ld_u32<RO>(w + s * 4 + 1), sh));
+	}
+	return acc;
+}
+
+// Final, lib/lz4ada.adb:993-1017: `tail` points at the < 16 bytes left after the stripes.
+template <bool RO>
+__device__ __forceinline__ uint32_t xxh_finish(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+					       uint64_t total_len, const uint8_t *tail, uint32_t rem)
+{
+	uint32_t h = total_len >= 16 ? rotl32(a0, 1) + rotl32(a1, 7) + rotl32(a2, 12) + rotl32(a3, 18)
+				     : a2 + PRIME_5;
+	h += static_cast<uint32_t>(total_len);
+	while (rem >= 4) {
+		uint32_t x = ld_u8<RO>(tail) | (ld_u8<RO>(tail + 1) << 8) | (ld_u8<RO>(tail + 2) << 16) |
+			     (ld_u8<RO>(tail + 3) << 24);
+		h = rotl32(h + x * PRIME_3, 17) * PRIME_4;
+		tail += 4;
+		rem -= 4;
+	}
+	while (rem) {
+		h = rotl32(h + ld_u8<RO>(tail) * PRIME_5, 11) * PRIME_1;
+		tail += 1;
+		rem -= 1;
+	}
+	h = (h ^ (h >> 15)) * PRIME_2;
+	h = (h ^ (h >> 13)) * PRIME_3;
+	return h ^ (h >> 16);
+}
+
+template <bool RO, bool PREFETCH>
+__device__ __forceinline__ uint32_t quad_xxh32(const uint8_t *p, uint64_t n, int lane)
+{
+	const int sub = lane & 3;
+	const uint64_t nstripes = n >> 4;
+	uint32_t acc = quad_stripes<RO, PREFETCH>(p, nstripes, xxh_init_acc(sub), sub);
+	const uint32_t a0 = __shfl_sync(FULL_MASK, acc, 0, 4);
+	const uint32_t a1 = __shfl_sync(FULL_MASK, acc, 1, 4);
+	const uint32_t a2 = __shfl_sync(FULL_MASK, acc, 2, 4);
+	const uint32_t a3 = __shfl_sync(FULL_MASK, acc, 3, 4);
+	return xxh_finish<RO>(a0, a1, a2, a3, n, p + (nstripes << 4), static_cast<uint32_t>(n & 15));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative copies (Write_Output, lib/lz4ada.adb:790-824 -- but exact: nothing is ever
+// written outside [dst, dst + n)).  Requires dst - src >= n or disjoint buffers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 shift_combine(const uint4 &A, const uint4 &B, uint32_t ws, uint32_t bs)
+{
+	uint32_t w0, w1, w2, w3, w4;
+	switch (ws) {   // warp-uniform
+	case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; break;
+	case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; break;
+	case 2: w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; break;
+	default: w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; break;
+	}
+	return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs),
+			  __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+}
+
+template <bool RO>
+__device__ __noinline__ void warp_copy_long(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	// head: bring dst to a 16-byte boundary
+	const uint32_t head = (16u - static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
+	if (lane < head) dst[lane] = static_cast<uint8_t>(ld_u8<RO>(src + lane));
+	dst += head;
+	src += head;
+	n -= head;
+	const uint32_t nvec = n >> 4;
+	const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15);
+	const uint4 *s4 = reinterpret_cast<const uint4 *>(src - m);
+	uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+	uint32_t v = lane;
+	if (m == 0) {
+		for (; v + 96 < nvec; v += 128) {   // 4 x 512 B in flight per warp
+			uint4 r0 = ld_u128<RO>(s4 + v), r1 = ld_u128<RO>(s4 + v + 32);
+			uint4 r2 = ld_u128<RO>(s4 + v + 64), r3 = ld_u128<RO>(s4 + v + 96);
+			d4[v] = r0; d4[v + 32] = r1; d4[v + 64] = r2; d4[v + 96] = r3;
+		}
+		for (; v < nvec; v += 32) d4[v] = ld_u128<RO>(s4 + v);
+	} else {
+		const uint32_t ws = m >> 2, bs = (m & 3) * 8;
+		for (; v + 32 < nvec; v += 64) {
+			uint4 a0 = ld_u128<RO>(s4 + v), b0 = ld_u128<RO>(s4 + v + 1);
+			uint4 a1 = ld_u128<RO>(s4 + v + 32), b1 = ld_u128<RO>(s4 + v + 33);
+			d4[v] = shift_combine(a0, b0, ws, bs);
+			d4[v + 32] = shift_combine(a1, b1, ws, bs);
+		}
+		for (; v < nvec; v += 32) d4[v] = shift_combine(ld_u128<RO>(s4 + v), ld_u128<RO>(s4 + v + 1), ws, bs);
+	}
+	const uint32_t done = nvec << 4, tail = n & 15;
+	if (lane < tail) dst[done + lane] = static_cast<uint8_t>(ld_u8<RO>(src + done + lane));
+}
+
+template <bool RO>
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	if (n <= 32) {
+		if (lane < n) dst[lane] = static_cast<uint8_t>(ld_u8<RO>(src + lane));
+	} else if (n < 128) {
+		for (uint32_t i = lane; i < n; i += 32) dst[i] = static_cast<uint8_t>(ld_u8<RO>(src + i));
+	} else {
+		warp_copy_long<RO>(dst, src, n, lane);
+	}
+}
+
+// Match copy: dst[0 .. ml) = dst[-offset ...] with LZ4 overlap semantics
+// (Output_With_History, lib/lz4ada.adb:845-904, phases I and R; phase H is the same
+// backwards read because the output is flat).
+__device__ __noinline__ void match_copy_overlap(uint8_t *d, uint32_t offset, uint32_t ml, int lane)
+{
+	uint32_t done = 0;
+	if (offset < 32) {
+		// first bytes straight from the pattern: d[i] = pattern[i mod offset]
+		const uint32_t m0 = ml < 32 ? ml : 32;
+		if (lane < m0) d[lane] = *(d - offset + (static_cast<uint32_t>(lane) % offset));
+		done = m0;
+		if (done == ml) return;
+		__syncwarp();
+		if ((offset & (offset - 1)) == 0 && offset <= 16 && ml - done >= 64) {
+			// period divides 16: every 16-byte aligned vector of the run is the same
+			// register pattern -> store-only replication (RLE runs, zero pages)
+			uint8_t *A = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(d) + 15) & ~uintptr_t(15));
+			const uint4 V = *reinterpret_cast<const uint4 *>(A);   // A + 16 <= d + 32: materialised
+			uint4 *body = reinterpret_cast<uint4 *>(A + 16);
+			uint8_t *end = d + ml;
+			const uint32_t nvec = static_cast<uint32_t>(end - (A + 16)) >> 4;
+			uint32_t v = lane;
+			for (; v + 96 < nvec; v += 128) {
+				body[v] = V; body[v + 32] = V; body[v + 64] = V; body[v + 96] = V;
+			}
+			for (; v < nvec; v += 32) body[v] = V;
+			uint8_t *T = A + 16 + (static_cast<size_t>(nvec) << 4);
+			const uint32_t tail = static_cast<uint32_t>(end - T);
+			if (lane < tail) T[lane] = A[lane];
+			return;
+		}
+	}
+	// doubling: L = largest multiple of the period not exceeding the bytes already valid
+	while (done < ml) {
+		const uint32_t avail = offset + done;
+		const uint32_t L = avail - (avail % offset);
+		const uint32_t chunk = (ml - done) < L ? (ml - done) : L;
+		warp_copy<false>(d + done, d + done - L, chunk, lane);
+		done += chunk;
+		if (done < ml) __syncwarp();
+	}
+}
+
+__device__ __forceinline__ void match_copy(uint8_t *d, uint32_t offset, uint32_t ml, int lane)
+{
+	__syncwarp();   // earlier stores of other lanes must be visible to the loads below
+	if (offset >= ml) {
+		warp_copy<false>(d, d - offset, ml, lane);
+	} else {
+		match_copy_overlap(d, offset, ml, lane);
+	}
+}
+
+// Process_Variable_Length, lib/lz4ada.adb:724-735: add bytes until one /= 255.  32 bytes per step
+// with a ballot for the first non-255 (z9m has 16 448 0xff bytes in one length).
+// Returns false when the extension runs past the end of the block.
+__device__ __forceinline__ bool read_length_ext(const uint8_t *src, uint32_t &ip, uint32_t iend,
+						uint32_t &len, int lane)
+{
+	for (;;) {
+		const uint32_t idx = ip + lane;
+		const uint32_t b = idx < iend ? ld_u8<true>(src + idx) : 0x100u;
+		const uint32_t stop = __ballot_sync(FULL_MASK, b != 255u);
+		if (stop == 0) {
+			len += 255u * 32u;
+			ip += 32;
+			continue;
+		}
+		const int first = __ffs(stop) - 1;
+		const uint32_t bv = __shfl_sync(FULL_MASK, b, first);
+		if (bv == 0x100u) return false;
+		len += 255u * first + bv;
+		ip += first + 1;
+		return true;
+	}
+}
+
+struct BlockResult {
+	uint32_t code;
+	uint32_t out_len;
+	uint32_t err_pos;
+	int32_t  aux;
+};
+
+// Decompress_Full_Block / Decompress_Sequence, lib/lz4ada.adb:716-788, one warp per block.
+// All lanes walk the token stream in lock-step (warp-uniform control flow, broadcast loads);
+// literal and match bytes are moved by the whole warp.
+// `o` = where this block's output starts, `hist` = bytes before `o` that belong to the same frame.
+// ALLOW_HIST = the bytes before `o` are already final (linked frames decoded in order).
+template <bool ALLOW_HIST>
+__device__ __forceinline__ BlockResult decode_lz4_block(const uint8_t *__restrict__ src, uint32_t n,
+							uint8_t *o, uint32_t cap, uint32_t hist, int lane)
+{
+	BlockResult r = {LZ4B200_ST_OK, 0, 0, 0};
+	uint32_t ip = 0, op = 0;
+	while (ip < n) {
+		const uint32_t token = ld_u8<true>(src + ip);
+		ip += 1;
+		uint32_t lit = token >> 4;
+		if (lit == 15 && !read_length_ext(src, ip, n, lit, lane)) {
+			r.code = LZ4B200_ST_LIT_EXT_OVERRUN; r.err_pos = op; break;
+		}
+		if (lit > 0) {
+			if (lit > n - ip) {
+				// reference: reads past the block, then reports :754 if the nibble /= 0
+				r.code = (token & 15) ? LZ4B200_ST_ENDS_AFTER_LITERALS : LZ4B200_ST_LITERAL_OVERRUN;
+				r.aux = (token & 15) ? static_cast<int32_t>(token & 15) : static_cast<int32_t>(n - ip);
+				r.err_pos = op + lit;   // content-size accounting already saw these bytes
+				r.out_len = lit;        // reported in the LITERAL_OVERRUN message
+				break;
+			}
+			if (lit > cap - op) { r.code = LZ4B200_ST_OUTPUT_OVERFLOW; r.err_pos = op + lit; break; }
+			warp_copy<true>(o + op, src + ip, lit, lane);
+			ip += lit;
+			op += lit;
+		}
+		if (ip >= n) {   // :752-764
+			if (token & 15) {
+				r.code = LZ4B200_ST_ENDS_AFTER_LITERALS; r.aux = token & 15; r.err_pos = op;
+			}
+			break;
+		}
+		if (ip + 1 >= n) { r.code = LZ4B200_ST_OFFSET_TRUNCATED; r.err_pos = op; break; }
+		const uint32_t offset = ld_u8<true>(src + ip) | (ld_u8<true>(src + ip + 1) << 8);
+		ip += 2;
+		if (offset == 0) { r.code = LZ4B200_ST_OFFSET_ZERO; r.err_pos = op; break; }
+		uint32_t ml = token & 15;
+		if (ml == 15 && !read_length_ext(src, ip, n, ml, lane)) {
+			r.code = LZ4B200_ST_MATCH_EXT_OVERRUN; r.err_pos = op; break;
+		}
+		ml += 4;
+		if (offset > op) {
+			// reaches before this block: legal only inside the frame's history (:864-874)
+			if (hist != 0xffffffffu && offset - op > hist) {
+				r.code = LZ4B200_ST_BACKREF_RANGE;
+				r.aux = static_cast<int32_t>(hist + op) - static_cast<int32_t>(offset);
+				r.err_pos = op;
+				break;
+			}
+			if (!ALLOW_HIST) { r.code = LZ4B200_ST_NEEDS_HISTORY; r.err_pos = op; break; }
+		}
+		if (ml > cap - op) { r.code = LZ4B200_ST_OUTPUT_OVERFLOW; r.err_pos = op + ml; break; }
+		match_copy(o + op, offset, ml, lane);
+		op += ml;
+	}
+	if (r.code == LZ4B200_ST_OK) r.out_len = op;
+	return r;
+}
+
+// One block, start to finish, by one warp: optional fused block checksum over the payload
+// (Check_Checksum, lib/lz4ada.adb:698-707 -- verified before any decoding, :672-676), then
+// either the stored copy (:685-695) or the LZ4 decode.
+template <bool ALLOW_HIST>
+__device__ __forceinline__ void process_block(const uint8_t *__restrict__ src_base, uint8_t *o,
+					      const lz4b200_blk_desc &d, uint32_t cap, uint32_t hist,
+					      lz4b200_blk_status *st, int lane)
+{
+	const uint8_t *s = src_base + d.src_off;
+	uint32_t computed = 0, declared = 0;
+	BlockResult r = {LZ4B200_ST_OK, 0, 0, 0};
+	if (d.flags & LZ4B200_BLK_HAS_CHECKSUM) {
+		const uint8_t *t = s + d.src_len;
+		declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) |
+			   (ld_u8<true>(t + 3) << 24);
+		computed = quad_xxh32<true, false>(s, d.src_len, lane);
+		if (computed != declared) r.code = LZ4B200_ST_BLOCK_CHECKSUM;
+	}
+	if (r.code == LZ4B200_ST_OK && !(d.flags & LZ4B200_BLK_HASH_ONLY)) {
+		if (d.flags & LZ4B200_BLK_STORED) {
+			if (d.src_len > cap) {
+				r.code = LZ4B200_ST_OUTPUT_OVERFLOW; r.err_pos = d.src_len;
+			} else {
+				warp_copy<true>(o, s, d.src_len, lane);
+				r.out_len = d.src_len;
+			}
+		} else {
+			r = decode_lz4_block<ALLOW_HIST>(s, d.src_len, o, cap, hist, lane);
+		}
+	}
+	if (lane == 0) {
+		st->code = r.code;
+		st->out_len = r.out_len;
+		st->err_pos = r.err_pos;
+		st->aux = r.aux;
+		st->xxh32_computed = computed;
+		st->xxh32_declared = declared;
+	}
+}
+
+}  // namespace lz4b200

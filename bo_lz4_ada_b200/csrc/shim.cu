@@ -1,0 +1,609 @@
+// shim.cu -- the lz4b200_* half of include/lz4b200.h: device context, memory, transfers and the
+// kernel launches K1..K5.  Compiled by nvcc for sm_100a only; everything exported is extern "C".
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "kernels.cuh"
+#include "lz4b200.h"
+
+using namespace lz4b200;
+
+// ------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------
+
+constexpr int K1_WARPS = 4;   // warps per CTA, one block per warp
+
+// K1 (+K2): independent blocks, one warp per block.
+__global__ void __launch_bounds__(K1_WARPS * 32)
+decode_blocks_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+		     const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t b = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+	if (b >= n_blocks) return;
+	const lz4b200_blk_desc d = desc[b];
+	if (d.flags & LZ4B200_BLK_CHAINED) return;
+	process_block<false>(src, dst + d.dst_off, d, d.dst_cap, d.hist_avail, status + b, lane);
+}
+
+// K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
+// simply reads backwards across block boundaries of its frame.
+__global__ void __launch_bounds__(K1_WARPS * 32)
+decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_chains,
+		     const lz4b200_chain *__restrict__ chains,
+		     const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t c = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+	if (c >= n_chains) return;
+	const lz4b200_chain ch = chains[c];
+	uint8_t *out = dst + ch.dst_off;
+	uint64_t pos = 0;         // chain-relative output position
+	uint64_t frame_start = 0; // chain-relative position where the current frame began
+	bool failed = false;
+	for (uint32_t i = 0; i < ch.n_blocks; i++) {
+		const uint32_t b = ch.first_block + i;
+		if (failed) {
+			if (lane == 0) {
+				status[b].code = LZ4B200_ST_NOT_RUN;
+				status[b].out_len = 0;
+				status[b].err_pos = 0;
+				status[b].aux = 0;
+				status[b].xxh32_computed = 0;
+				status[b].xxh32_declared = 0;
+			}
+			continue;
+		}
+		const lz4b200_blk_desc d = desc[b];
+		if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+		const uint64_t fpos = pos - frame_start;
+		const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
+		const uint64_t room = ch.dst_cap - pos;
+		const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+		process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
+		__syncwarp();
+		const uint32_t code = status[b].code;      // lane 0 wrote it; visible after __syncwarp
+		const uint32_t out_len = status[b].out_len;
+		if (code != LZ4B200_ST_OK) failed = true;
+		else pos += out_len;
+	}
+}
+
+// One block against a device-resident history window (single-block path under Update).
+__global__ void __launch_bounds__(32)
+stream_block_kernel(const uint8_t *__restrict__ src, uint8_t *win, const lz4b200_blk_desc *desc,
+		    lz4b200_blk_status *status)
+{
+	const int lane = threadIdx.x & 31;
+	const lz4b200_blk_desc d = *desc;
+	process_block<true>(src, win + d.dst_off, d, d.dst_cap, d.hist_avail, status, lane);
+}
+
+// K3: one XXH32 chain per byte range, eight ranges per warp (a quad each).
+__global__ void __launch_bounds__(128)
+xxh32_spans_kernel(const uint8_t *__restrict__ data, uint32_t n,
+		   const lz4b200_hash_span *__restrict__ spans, uint32_t *out)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint32_t idx = warp * 8 + (lane >> 2);
+	const bool valid = idx < n;
+	uint64_t off = 0, len = 0;
+	if (valid) {
+		off = spans[idx].off;
+		len = spans[idx].len;
+	}
+	const uint32_t h = quad_xxh32<true, true>(data + off, len, lane);
+	if (valid && (lane & 3) == 0) out[idx] = h;
+}
+
+// K3 (batch): content checksum per frame, length summed from the block statuses on the device.
+__global__ void __launch_bounds__(128)
+xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
+		    const lz4b200_frame_blocks *__restrict__ frames,
+		    const lz4b200_blk_desc *__restrict__ desc, const lz4b200_blk_status *__restrict__ status,
+		    uint32_t *digest, uint32_t *valid)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint32_t f = warp * 8 + (lane >> 2);
+	const bool have = f < n_frames;
+	uint64_t base = 0, len = 0;
+	bool okay = have;
+	if (have) {
+		const lz4b200_frame_blocks fb = frames[f];
+		if (fb.n_blocks) base = desc[fb.first_block].dst_off;
+		for (uint32_t i = 0; i < fb.n_blocks; i++) {
+			const uint32_t b = fb.first_block + i;
+			if (status[b].code != LZ4B200_ST_OK || desc[b].dst_off != base + len) {
+				okay = false;
+				break;
+			}
+			len += status[b].out_len;
+		}
+	}
+	if (!okay) len = 0;
+	const uint32_t h = quad_xxh32<true, true>(dst + base, len, lane);
+	if (have && (lane & 3) == 0) {
+		digest[f] = h;
+		valid[f] = okay ? 1u : 0u;
+	}
+}
+
+// Streaming content checksum for the single-block path under Update: the XXH32 state lives in
+// device memory between blocks (XXHash32.Update, lib/lz4ada.adb:942-977).
+__global__ void __launch_bounds__(32)
+xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest)
+{
+	const int lane = threadIdx.x & 31;
+	const int sub = lane & 3;
+	uint32_t acc = st->acc[sub];
+	uint32_t buf_size = st->buf_size;
+	const uint64_t total = st->total_len + len;
+	uint32_t pos = 0;
+	__syncwarp();
+	if (buf_size > 0 && len > 0) {
+		const uint32_t need = 16 - buf_size;
+		const uint32_t take = need < len ? need : len;
+		if (lane < take) st->buf[buf_size + lane] = data[lane];
+		__syncwarp();
+		buf_size += take;
+		pos = take;
+		if (buf_size == 16) {
+			const uint8_t *bp = st->buf + 4 * sub;
+			const uint32_t x = bp[0] | (bp[1] << 8) | (bp[2] << 16) | (bp[3] << 24);
+			acc = xxh_round(acc, x);
+			buf_size = 0;
+		}
+		__syncwarp();
+	}
+	const uint32_t nstripes = (len - pos) >> 4;
+	acc = quad_stripes<true, true>(data + pos, nstripes, acc, sub);
+	pos += nstripes << 4;
+	const uint32_t rem = len - pos;
+	if (rem > 0) {   // only reachable with buf_size == 0
+		if (lane < rem) st->buf[lane] = data[pos + lane];
+		buf_size = rem;
+	}
+	__syncwarp();
+	if (lane < 4) st->acc[lane] = acc;
+	if (lane == 0) {
+		st->buf_size = buf_size;
+		st->total_len = total;
+	}
+	if (digest != nullptr) {
+		const uint32_t a0 = __shfl_sync(FULL_MASK, acc, 0), a1 = __shfl_sync(FULL_MASK, acc, 1);
+		const uint32_t a2 = __shfl_sync(FULL_MASK, acc, 2), a3 = __shfl_sync(FULL_MASK, acc, 3);
+		const uint32_t h = xxh_finish<false>(a0, a1, a2, a3, total, st->buf, buf_size);
+		if (lane == 0) *digest = h;
+	}
+}
+
+__global__ void xxh32_stream_reset_kernel(XxhState *st)
+{
+	if (threadIdx.x < 4) st->acc[threadIdx.x] = xxh_init_acc(threadIdx.x);
+	if (threadIdx.x == 0) {
+		st->buf_size = 0;
+		st->total_len = 0;
+	}
+}
+
+// K5: size pre-pass, one thread per block: walks token / length / offset bytes only.
+__global__ void __launch_bounds__(128)
+size_blocks_kernel(const uint8_t *__restrict__ src, uint32_t n_blocks,
+		   const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status)
+{
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_blocks) return;
+	const lz4b200_blk_desc d = desc[b];
+	const uint8_t *s = src + d.src_off;
+	const uint32_t n = d.src_len;
+	uint32_t code = LZ4B200_ST_OK, err_pos = 0;
+	uint64_t op = 0;
+	if (d.flags & LZ4B200_BLK_STORED) {
+		op = n;
+	} else {
+		uint32_t ip = 0;
+		while (ip < n) {
+			const uint32_t token = __ldg(s + ip++);
+			uint32_t lit = token >> 4;
+			if (lit == 15) {
+				uint32_t bv;
+				do {
+					if (ip >= n) { code = LZ4B200_ST_LIT_EXT_OVERRUN; break; }
+					bv = __ldg(s + ip++);
+					lit += bv;
+				} while (bv == 255);
+				if (code) break;
+			}
+			if (lit > n - ip) {
+				code = (token & 15) ? LZ4B200_ST_ENDS_AFTER_LITERALS : LZ4B200_ST_LITERAL_OVERRUN;
+				break;
+			}
+			ip += lit;
+			op += lit;
+			if (ip >= n) {
+				if (token & 15) code = LZ4B200_ST_ENDS_AFTER_LITERALS;
+				break;
+			}
+			if (ip + 1 >= n) { code = LZ4B200_ST_OFFSET_TRUNCATED; break; }
+			const uint32_t offset = __ldg(s + ip) | (__ldg(s + ip + 1) << 8);
+			ip += 2;
+			if (offset == 0) { code = LZ4B200_ST_OFFSET_ZERO; break; }
+			uint32_t ml = token & 15;
+			if (ml == 15) {
+				uint32_t bv;
+				do {
+					if (ip >= n) { code = LZ4B200_ST_MATCH_EXT_OVERRUN; break; }
+					bv = __ldg(s + ip++);
+					ml += bv;
+				} while (bv == 255);
+				if (code) break;
+			}
+			op += ml + 4;
+		}
+		err_pos = op > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(op);
+	}
+	status[b].code = code;
+	status[b].out_len = op > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(op);
+	status[b].err_pos = err_pos;
+	status[b].aux = 0;
+	status[b].xxh32_computed = 0;
+	status[b].xxh32_declared = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------
+
+struct lz4b200_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	uint64_t launches = 0;
+	char err[256] = "";
+};
+
+static int fail(lz4b200_ctx *ctx, cudaError_t e, const char *what)
+{
+	if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+	return LZ4B200_ERR_CUDA;
+}
+
+#define CK(call)                                                                        \
+	do {                                                                            \
+		cudaError_t e_ = (call);                                                \
+		if (e_ != cudaSuccess) return fail(ctx, e_, #call);                     \
+	} while (0)
+
+extern "C" {
+
+int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
+{
+	if (!out) return LZ4B200_ERR_ARG;
+	*out = nullptr;
+	lz4b200_ctx *ctx = new (std::nothrow) lz4b200_ctx();
+	if (!ctx) return LZ4B200_ERR_NOMEM;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || device < 0 || device >= ndev) {
+		// no CUDA device: there is deliberately no CPU fallback
+		delete ctx;
+		return LZ4B200_ERR_CUDA;
+	}
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LZ4B200_ERR_CUDA; }
+	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (stream) {
+		ctx->stream = static_cast<cudaStream_t>(stream);
+	} else {
+		if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+			delete ctx;
+			return LZ4B200_ERR_CUDA;
+		}
+		ctx->own_stream = true;
+	}
+	cudaEventCreate(&ctx->ev0);
+	cudaEventCreate(&ctx->ev1);
+	*out = ctx;
+	return LZ4B200_OK;
+}
+
+int lz4b200_destroy(lz4b200_ctx *ctx)
+{
+	if (!ctx) return LZ4B200_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return LZ4B200_OK;
+}
+
+const char *lz4b200_last_error(const lz4b200_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+int lz4b200_sm_count(const lz4b200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr)
+{
+	if (!ctx || !dev_ptr) return LZ4B200_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMalloc(dev_ptr, bytes + 64));   // slack: aligned 16-byte loads may touch the granule past the end
+	return LZ4B200_OK;
+}
+
+int lz4b200_free(lz4b200_ctx *ctx, void *dev_ptr)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaFree(dev_ptr));
+	return LZ4B200_OK;
+}
+
+int lz4b200_alloc_host(lz4b200_ctx *ctx, size_t bytes, void **host_ptr)
+{
+	if (!ctx || !host_ptr) return LZ4B200_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMallocHost(host_ptr, bytes ? bytes : 1));
+	return LZ4B200_OK;
+}
+
+int lz4b200_free_host(lz4b200_ctx *ctx, void *host_ptr)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	CK(cudaFreeHost(host_ptr));
+	return LZ4B200_OK;
+}
+
+int lz4b200_h2d(lz4b200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (bytes == 0) return LZ4B200_OK;
+	CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_d2h(lz4b200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (bytes == 0) return LZ4B200_OK;
+	CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_memset(lz4b200_ctx *ctx, void *dst_dev, int value, size_t bytes)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (bytes == 0) return LZ4B200_OK;
+	CK(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_sync(lz4b200_ctx *ctx)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	CK(cudaStreamSynchronize(ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_timer_start(lz4b200_ctx *ctx)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	CK(cudaEventRecord(ctx->ev0, ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms)
+{
+	if (!ctx || !elapsed_ms) return LZ4B200_ERR_ARG;
+	CK(cudaEventRecord(ctx->ev1, ctx->stream));
+	CK(cudaEventSynchronize(ctx->ev1));
+	CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+	return LZ4B200_OK;
+}
+
+int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t n_blocks,
+			  const lz4b200_blk_desc *desc, lz4b200_blk_status *status)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (n_blocks == 0) return LZ4B200_OK;
+	const uint32_t grid = (n_blocks + K1_WARPS - 1) / K1_WARPS;
+	decode_blocks_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t n_chains,
+			  const lz4b200_chain *chains, const lz4b200_blk_desc *desc,
+			  lz4b200_blk_status *status)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (n_chains == 0) return LZ4B200_OK;
+	const uint32_t grid = (n_chains + K1_WARPS - 1) / K1_WARPS;
+	decode_linked_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames,
+			 const lz4b200_frame_blocks *frames, const lz4b200_blk_desc *desc,
+			 const lz4b200_blk_status *status, uint32_t *digest, uint32_t *valid)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (n_frames == 0) return LZ4B200_OK;
+	const uint32_t warps = (n_frames + 7) / 8;
+	xxh32_frames_kernel<<<(warps + 3) / 4, 128, 0, ctx->stream>>>(dst, n_frames, frames, desc, status, digest,
+								       valid);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_xxh32_spans(lz4b200_ctx *ctx, const uint8_t *data, uint32_t n,
+			const lz4b200_hash_span *spans, uint32_t *out)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (n == 0) return LZ4B200_OK;
+	const uint32_t warps = (n + 7) / 8;
+	const uint32_t grid = (warps + 3) / 4;
+	xxh32_spans_kernel<<<grid, 128, 0, ctx->stream>>>(data, n, spans, out);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_size_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint32_t n_blocks,
+			const lz4b200_blk_desc *desc, lz4b200_blk_status *status)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (n_blocks == 0) return LZ4B200_OK;
+	size_blocks_kernel<<<(n_blocks + 127) / 128, 128, 0, ctx->stream>>>(src, n_blocks, desc, status);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-block streaming path under Decompressor.Update
+// ------------------------------------------------------------------------------------------
+
+struct lz4b200_stream {
+	lz4b200_ctx *ctx = nullptr;
+	uint32_t max_block = 0;        // largest payload / output of one call
+	uint8_t *d_src = nullptr;      // payload (+4 checksum bytes) of the current block
+	uint8_t *d_win = nullptr;      // [history | blocks ...] flat window
+	size_t win_size = 0;
+	size_t cursor = 0;             // where the next block's output goes inside d_win
+	uint64_t frame_pos = 0;        // bytes of the current frame produced so far
+	uint8_t *d_meta = nullptr;     // blk_desc | blk_status | XxhState | digest
+	uint8_t *h_meta = nullptr;     // pinned mirror
+};
+
+constexpr size_t HISTORY = 65536;
+constexpr size_t META_DESC = 0, META_STATUS = 64, META_XXH = 128, META_DIGEST = 192, META_BYTES = 256;
+
+int lz4b200_stream_create(lz4b200_ctx *ctx, uint32_t max_block, lz4b200_stream **out)
+{
+	if (!ctx || !out) return LZ4B200_ERR_ARG;
+	lz4b200_stream *s = new (std::nothrow) lz4b200_stream();
+	if (!s) return LZ4B200_ERR_NOMEM;
+	s->ctx = ctx;
+	s->max_block = max_block;
+	s->win_size = HISTORY + 2 * static_cast<size_t>(max_block) + 256;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMalloc(&s->d_src, static_cast<size_t>(max_block) + 64));
+	CK(cudaMalloc(&s->d_win, s->win_size + 64));
+	CK(cudaMalloc(&s->d_meta, META_BYTES));
+	CK(cudaMallocHost(&s->h_meta, META_BYTES));
+	s->cursor = HISTORY;
+	xxh32_stream_reset_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH));
+	ctx->launches++;
+	CK(cudaGetLastError());
+	*out = s;
+	return LZ4B200_OK;
+}
+
+int lz4b200_stream_destroy(lz4b200_stream *s)
+{
+	if (!s) return LZ4B200_OK;
+	cudaSetDevice(s->ctx->device);
+	cudaStreamSynchronize(s->ctx->stream);
+	cudaFree(s->d_src);
+	cudaFree(s->d_win);
+	cudaFree(s->d_meta);
+	cudaFreeHost(s->h_meta);
+	delete s;
+	return LZ4B200_OK;
+}
+
+int lz4b200_stream_reset(lz4b200_stream *s)
+{
+	if (!s) return LZ4B200_ERR_ARG;
+	lz4b200_ctx *ctx = s->ctx;
+	s->cursor = HISTORY;
+	s->frame_pos = 0;
+	xxh32_stream_reset_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH));
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len, uint32_t flags,
+			 int hash_content, uint8_t *host_dst, uint32_t dst_cap,
+			 lz4b200_blk_status *status)
+{
+	if (!s || !status) return LZ4B200_ERR_ARG;
+	lz4b200_ctx *ctx = s->ctx;
+	const uint32_t trailer = (flags & LZ4B200_BLK_HAS_CHECKSUM) ? 4u : 0u;
+	if (static_cast<uint64_t>(src_len) + trailer > static_cast<uint64_t>(s->max_block) + 8 ||
+	    dst_cap > s->max_block)
+		return LZ4B200_ERR_ARG;
+	// keep the last 64 KiB in front of the cursor; compact when the window is exhausted
+	if (s->cursor + dst_cap > s->win_size) {
+		CK(cudaMemcpyAsync(s->d_win, s->d_win + s->cursor - HISTORY, HISTORY, cudaMemcpyDeviceToDevice,
+				   ctx->stream));
+		s->cursor = HISTORY;
+	}
+	CK(cudaMemcpyAsync(s->d_src, host_src, static_cast<size_t>(src_len) + trailer, cudaMemcpyHostToDevice,
+			   ctx->stream));
+	lz4b200_blk_desc *hd = reinterpret_cast<lz4b200_blk_desc *>(s->h_meta + META_DESC);
+	hd->src_off = 0;
+	hd->dst_off = s->cursor;
+	hd->src_len = src_len;
+	hd->dst_cap = dst_cap;
+	hd->flags = flags;
+	hd->hist_avail = s->frame_pos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(s->frame_pos);
+	CK(cudaMemcpyAsync(s->d_meta + META_DESC, hd, sizeof *hd, cudaMemcpyHostToDevice, ctx->stream));
+	// the history in front of the cursor is final: matches may read backwards across the
+	// block boundary (ALLOW_HIST)
+	stream_block_kernel<<<1, 32, 0, ctx->stream>>>(
+		s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC),
+		reinterpret_cast<lz4b200_blk_status *>(s->d_meta + META_STATUS));
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(s->h_meta + META_STATUS, s->d_meta + META_STATUS, sizeof(lz4b200_blk_status),
+			   cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	*status = *reinterpret_cast<lz4b200_blk_status *>(s->h_meta + META_STATUS);
+	if (status->code != LZ4B200_ST_OK) return LZ4B200_OK;
+	const uint32_t n = status->out_len;
+	if (n > 0) {
+		if (hash_content) {
+			xxh32_stream_kernel<<<1, 32, 0, ctx->stream>>>(
+				reinterpret_cast<XxhState *>(s->d_meta + META_XXH), s->d_win + s->cursor, n, nullptr);
+			ctx->launches++;
+			CK(cudaGetLastError());
+		}
+		CK(cudaMemcpyAsync(host_dst, s->d_win + s->cursor, n, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	s->cursor += n;
+	s->frame_pos += n;
+	return LZ4B200_OK;
+}
+
+int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32)
+{
+	if (!s || !xxh32) return LZ4B200_ERR_ARG;
+	lz4b200_ctx *ctx = s->ctx;
+	xxh32_stream_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH),
+						       s->d_win, 0, reinterpret_cast<uint32_t *>(s->d_meta + META_DIGEST));
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(s->h_meta + META_DIGEST, s->d_meta + META_DIGEST, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	*xxh32 = *reinterpret_cast<uint32_t *>(s->h_meta + META_DIGEST);
+	return LZ4B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+/*
+ * lz4b200.h -- C-ABI of the B200-native LZ4 decompressor (liblz4b200.so).
+ *
+ * Two layers, both plain C (pointers and sizes only, no C++/torch types, no
+ * callbacks, no exceptions across the boundary):
+ *
+ *   lz4b200_*  the device shim.  This is what the Ada host layer binds with
+ *              `pragma Import (C, ...)`: context, device
+ *              buffers, transfers and the kernel launches K1..K5.  It has no
+ *              counterpart in the reference (which is CPU-only); each entry
+ *              names the reference code whose work it takes over.
+ *   lz4ada_*   the LZ4Ada package API (reference lib/lz4ada.ads:50-344) with
+ *              the same names, argument meaning and error behaviour, written
+ *              in C++ above the shim because this image has no Ada compiler.
+ *              Ada exceptions become a return code (enum lz4ada_exception)
+ *              plus the exact GNAT Exception_Information line.
+ *
+ * There is no CPU decode path behind any of these calls: block payloads are
+ * only ever decoded by the sm_100a kernels.  If the CUDA runtime or a device
+ * is missing every call fails with LZ4B200_ERR_CUDA.
+ */
+#ifndef LZ4B200_H
+#define LZ4B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ4B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------
+ * Device shim
+ * --------------------------------------------------------------------- */
+
+/* Return codes of every lz4b200_* call.  LZ4 *data* errors never travel here;
+ * they are reported per block in lz4b200_blk_status. */
+enum lz4b200_rc {
+	LZ4B200_OK          = 0,
+	LZ4B200_ERR_CUDA    = -1,   /* CUDA runtime/driver failure; see lz4b200_last_error */
+	LZ4B200_ERR_ARG     = -2,
+	LZ4B200_ERR_NOMEM   = -3
+};
+
+typedef struct lz4b200_ctx lz4b200_ctx;
+
+/* One descriptor per LZ4 block, built by the host block-table builder from the
+ * 4-byte size words the reference reads in Try_Detect_Input_Length
+ * (lib/lz4ada.adb:525-585).  Offsets are relative to the src / dst base
+ * pointers given to the launch. */
+typedef struct lz4b200_blk_desc {
+	uint64_t src_off;     /* first payload byte (after the size word) */
+	uint64_t dst_off;     /* where this block's output starts */
+	uint32_t src_len;     /* payload bytes, excluding the optional checksum trailer */
+	uint32_t dst_cap;     /* output bytes this block may produce */
+	uint32_t flags;       /* LZ4B200_BLK_* */
+	uint32_t hist_avail;  /* bytes of this frame's output that precede dst_off and may be
+	                       * referenced (frame position of the block start; 0xffffffff once
+	                       * the reference's 64 KiB ring has wrapped, lib/lz4ada.adb:864) */
+} lz4b200_blk_desc;
+
+#define LZ4B200_BLK_STORED        1u  /* size word bit 31 set, lib/lz4ada.adb:536-537 */
+#define LZ4B200_BLK_HAS_CHECKSUM  2u  /* 4-byte LE XXH32 trailer follows the payload, :672-676 */
+#define LZ4B200_BLK_HASH_ONLY     4u  /* verify checksum, do not decode (used by retries) */
+#define LZ4B200_BLK_CHAINED       8u  /* decoded in order by lz4b200_decode_linked; K1 skips it */
+#define LZ4B200_BLK_FIRST_OF_FRAME 16u /* chain kernel: a new frame starts here, history restarts */
+
+/* Per-block outcome written by the kernels; the host folds these in stream
+ * order into the reference's exceptions. */
+typedef struct lz4b200_blk_status {
+	uint32_t code;            /* LZ4B200_ST_* */
+	uint32_t out_len;         /* bytes produced (valid when code == OK) */
+	uint32_t err_pos;         /* block-relative output position when the error was detected
+	                           * (after the literals of the failing sequence) */
+	int32_t  aux;             /* value the reference prints: raw match nibble (:754),
+	                           * frame_pos - offset (:868) */
+	uint32_t xxh32_computed;  /* block checksum as computed (when HAS_CHECKSUM) */
+	uint32_t xxh32_declared;  /* block checksum as stored in the trailer */
+} lz4b200_blk_status;
+
+enum lz4b200_status_code {
+	LZ4B200_ST_OK                  = 0,
+	LZ4B200_ST_BLOCK_CHECKSUM      = 1,  /* lib/lz4ada.adb:702 */
+	LZ4B200_ST_ENDS_AFTER_LITERALS = 2,  /* :754 */
+	LZ4B200_ST_OFFSET_ZERO         = 3,  /* :770 */
+	LZ4B200_ST_BACKREF_RANGE       = 4,  /* :868 */
+	LZ4B200_ST_LITERAL_OVERRUN     = 5,  /* literal run past block end with nibble 0 (ref: silent garbage) */
+	LZ4B200_ST_LIT_EXT_OVERRUN     = 6,  /* length extension past block end (ref: Constraint_Error) */
+	LZ4B200_ST_MATCH_EXT_OVERRUN   = 7,
+	LZ4B200_ST_OFFSET_TRUNCATED    = 8,  /* block ends inside the 2-byte offset (ref: Constraint_Error) */
+	LZ4B200_ST_OUTPUT_OVERFLOW     = 9,  /* would write past dst_cap (ref: unchecked write) */
+	LZ4B200_ST_NEEDS_HISTORY       = 10, /* not an error: a block decoded independently reaches into
+	                                      * the previous block; the host re-runs the frame through
+	                                      * lz4b200_decode_linked (reference accepts such frames) */
+	LZ4B200_ST_NOT_RUN             = 11  /* linked frame: an earlier block of the frame failed */
+};
+
+/* A run of consecutive block descriptors decoded strictly in order by one warp, each block's
+ * output starting where the previous one ended: one linked frame, or a whole stream of frames
+ * that needs exact placement (LZ4B200_BLK_FIRST_OF_FRAME restarts the history). */
+typedef struct lz4b200_chain {
+	uint32_t first_block;
+	uint32_t n_blocks;
+	uint64_t dst_off;   /* output of the chain starts here ... */
+	uint64_t dst_cap;   /* ... and may not grow beyond this many bytes */
+} lz4b200_chain;
+
+/* The blocks of one frame, for the content checksum over their concatenated output. */
+typedef struct lz4b200_frame_blocks {
+	uint32_t first_block;
+	uint32_t n_blocks;
+} lz4b200_frame_blocks;
+
+/* A byte range to hash (content checksum of one frame), relative to `data`. */
+typedef struct lz4b200_hash_span {
+	uint64_t off;
+	uint64_t len;
+} lz4b200_hash_span;
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t the
+ * caller owns (e.g. torch's current stream) or NULL to let the context create
+ * its own non-blocking stream.  A context is used by one host thread at a time. */
+int lz4b200_create(int device, void *stream, lz4b200_ctx **out);
+int lz4b200_destroy(lz4b200_ctx *ctx);
+/* Text of the last CUDA failure seen by this context (never NULL). */
+const char *lz4b200_last_error(const lz4b200_ctx *ctx);
+/* SM count of the context's device (grid sizing is a multiple of it). */
+int lz4b200_sm_count(const lz4b200_ctx *ctx);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx);
+
+/* Device and pinned-host memory, so that the Ada side never links libcudart. */
+int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr);
+int lz4b200_free(lz4b200_ctx *ctx, void *dev_ptr);
+int lz4b200_alloc_host(lz4b200_ctx *ctx, size_t bytes, void **host_ptr);
+int lz4b200_free_host(lz4b200_ctx *ctx, void *host_ptr);
+/* Asynchronous on the context stream; pair with lz4b200_sync. */
+int lz4b200_h2d(lz4b200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int lz4b200_d2h(lz4b200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int lz4b200_memset(lz4b200_ctx *ctx, void *dst_dev, int value, size_t bytes);
+int lz4b200_sync(lz4b200_ctx *ctx);
+
+/* Device-side timing on the context stream (CUDA events). */
+int lz4b200_timer_start(lz4b200_ctx *ctx);
+int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms);   /* synchronises */
+
+/* K1 (+K2): decode `n_blocks` mutually independent blocks, one warp per block,
+ * block XXH32 fused.  Takes over Decode_Full_Block_With_Trailer,
+ * Check_Checksum, Decompress_Full_Block, Write_Output and Output_With_History
+ * (lib/lz4ada.adb:661-904).  All pointers are device pointers. */
+int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst,
+		uint32_t n_blocks, const lz4b200_blk_desc *desc,
+		lz4b200_blk_status *status);
+
+/* K4: chains -- blocks in order by one warp, chains in parallel; the running output
+ * position of the chain places every block, so matches may reach back across block
+ * boundaries of the same frame (linked frames; also the exact-placement retry path).
+ * Replaces the ring/history handling of lib/lz4ada.adb:678-680, 845-904. */
+int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst,
+		uint32_t n_chains, const lz4b200_chain *chains,
+		const lz4b200_blk_desc *desc, lz4b200_blk_status *status);
+
+/* K3: XXH32 (seed 0) of `n` byte ranges, one serial chain per range, ranges in
+ * parallel.  Takes over Update_Checksum / XXHash32.Update / Final for the
+ * content checksum (lib/lz4ada.adb:709-714, 942-1017). */
+int lz4b200_xxh32_spans(lz4b200_ctx *ctx, const uint8_t *data, uint32_t n,
+		const lz4b200_hash_span *spans, uint32_t *out);
+
+/* K3 for the batch path: content checksum of each frame straight after K1/K4 without a
+ * host round trip -- the length of a frame's output is summed from the block statuses on
+ * the device.  valid[f] = 0 when a block of the frame failed or the blocks' outputs are not
+ * contiguous (the host then re-places the frame and asks again). */
+int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames,
+		const lz4b200_frame_blocks *frames, const lz4b200_blk_desc *desc,
+		const lz4b200_blk_status *status, uint32_t *digest, uint32_t *valid);
+
+/* K5: size pre-pass -- walks the sequences of each block without writing
+ * output and reports out_len (and structural errors) in status.  Used when a
+ * frame's interior blocks are not all block-max sized (the frame format
+ * carries no per-block decompressed size). */
+int lz4b200_size_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint32_t n_blocks,
+		const lz4b200_blk_desc *desc, lz4b200_blk_status *status);
+
+/* Synchronous single-block path under Decompressor.Update.  A stream object owns a
+ * device-resident window [64 KiB history | block output ...] and the streaming XXH32 state
+ * of the content checksum, so nothing but the new block crosses PCIe.  There is no CPU decode
+ * behind it.  max_block = largest payload / output of one call (block max + 64 KiB + 8 for a
+ * caller honouring Min_Buffer_Size). */
+typedef struct lz4b200_stream lz4b200_stream;
+int lz4b200_stream_create(lz4b200_ctx *ctx, uint32_t max_block, lz4b200_stream **out);
+int lz4b200_stream_destroy(lz4b200_stream *s);
+/* New frame: forget history, reset the content hash (Reset_Outer_For_Next_Frame, :451-461). */
+int lz4b200_stream_reset(lz4b200_stream *s);
+/* H2D of one block (payload + optional 4-byte checksum trailer), one warp decodes it behind
+ * the window's history, optional streaming content-hash update over the produced bytes,
+ * D2H of the produced bytes to host_dst.  flags = LZ4B200_BLK_*. */
+int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len,
+		uint32_t flags, int hash_content, uint8_t *host_dst, uint32_t dst_cap,
+		lz4b200_blk_status *status);
+/* XXH32 of every byte produced since the last reset (XXHash32.Final, :993-1017). */
+int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32);
+
+/* ------------------------------------------------------------------------
+ * LZ4Ada package API  (reference lib/lz4ada.ads)
+ * --------------------------------------------------------------------- */
+
+/* Flexible_Memory_Reservation, lib/lz4ada.ads:79-80 (same order) */
+enum lz4ada_reservation {
+	LZ4ADA_SZ_64_KIB = 0, LZ4ADA_SZ_256_KIB, LZ4ADA_SZ_1_MIB, LZ4ADA_SZ_4_MIB,
+	LZ4ADA_SZ_8_MIB, LZ4ADA_USE_FIRST, LZ4ADA_SINGLE_FRAME
+};
+#define LZ4ADA_FOR_MODERN LZ4ADA_SZ_4_MIB   /* lib/lz4ada.ads:92  */
+#define LZ4ADA_FOR_LEGACY LZ4ADA_SZ_8_MIB   /* lib/lz4ada.ads:100 */
+#define LZ4ADA_FOR_ALL    LZ4ADA_SZ_8_MIB   /* lib/lz4ada.ads:106 */
+
+/* End_Of_Frame, lib/lz4ada.ads:124 */
+enum lz4ada_end_of_frame { LZ4ADA_EOF_YES = 0, LZ4ADA_EOF_NO = 1, LZ4ADA_EOF_MAYBE = 2 };
+
+/* The five exceptions of lib/lz4ada.ads:133-162, plus the non-library outcomes. */
+enum lz4ada_exception {
+	LZ4ADA_OK = 0,
+	LZ4ADA_CHECKSUM_ERROR,
+	LZ4ADA_DATA_CORRUPTION,
+	LZ4ADA_NOT_SUPPORTED,
+	LZ4ADA_TOO_FEW_HEADER_BYTES,
+	LZ4ADA_TOO_LITTLE_MEMORY,
+	LZ4ADA_CONSTRAINT_ERROR,   /* "Library bug detected", lib/lz4ada.adb:185 */
+	LZ4ADA_ASSERTION_ERROR,    /* violated precondition (Pre => ...) */
+	LZ4ADA_DEVICE_ERROR        /* CUDA failure: distinct from every LZ4 error */
+};
+
+typedef struct lz4ada_decompressor lz4ada_decompressor;
+
+/* Bind the LZ4Ada layer of this thread/process to a device context.  Every
+ * decompressor created afterwards decodes its blocks on that device.  Passing
+ * NULL makes the library create (once) a context on device 0. */
+int lz4ada_set_device_context(lz4b200_ctx *ctx);
+
+/* Init, lib/lz4ada.ads:189/218, lib/lz4ada.adb:48-63 */
+int lz4ada_init(int *min_buffer_size, int reservation, lz4ada_decompressor **out);
+/* Init_With_Header, lib/lz4ada.ads:238, lib/lz4ada.adb:79-125.  Pre: input_len >= 7. */
+int lz4ada_init_with_header(const uint8_t *input, int input_len, int *num_consumed,
+		int *min_buffer_size, int reservation, lz4ada_decompressor **out,
+		char *message, size_t message_cap);
+/* Init_For_Block, lib/lz4ada.ads:255, lib/lz4ada.adb:127-147 */
+int lz4ada_init_for_block(int *min_buffer_size, int compressed_length, int reservation,
+		lz4ada_decompressor **out);
+/* Update (Octets flavour, Buffer'First = 0), lib/lz4ada.ads:281, lib/lz4ada.adb:383-418.
+ * One step per call exactly as the reference. */
+int lz4ada_update(lz4ada_decompressor *ctx, const uint8_t *input, int input_len,
+		int *num_consumed, uint8_t *buffer, int buffer_len,
+		int *output_first, int *output_last);
+/* Is_End_Of_Frame, lib/lz4ada.ads:303 */
+int lz4ada_is_end_of_frame(const lz4ada_decompressor *ctx);
+/* "raised LZ4ADA.<NAME> : <message>" of the last failing call on ctx. */
+const char *lz4ada_exception_message(const lz4ada_decompressor *ctx);
+void lz4ada_free(lz4ada_decompressor *ctx);
+
+/* To_Hex, lib/lz4ada.ads:306-307 (lower case, zero padded; out needs 3 / 9 bytes) */
+void lz4ada_to_hex_u8(uint8_t num, char *out);
+void lz4ada_to_hex_u32(uint32_t num, char *out);
+
+/* package XXHash32, lib/lz4ada.ads:311-321.  Host-side like the reference's:
+ * it serves the frame-header checksum and callers such as tool_xxhash32ada;
+ * block and content checksums of the decode path are computed on the device. */
+typedef struct lz4ada_xxhash32 {
+	uint32_t state[4];
+	uint8_t  buffer[16];
+	int32_t  buffer_size;
+	uint64_t total_length;
+} lz4ada_xxhash32;
+void     lz4ada_xxhash32_init(lz4ada_xxhash32 *h, uint32_t seed);   /* NB: ignores seed like :925-930 */
+void     lz4ada_xxhash32_reset(lz4ada_xxhash32 *h, uint32_t seed);
+void     lz4ada_xxhash32_update(lz4ada_xxhash32 *h, const uint8_t *input, size_t len);
+uint32_t lz4ada_xxhash32_final(const lz4ada_xxhash32 *h);
+uint32_t lz4ada_xxhash32_hash(const uint8_t *input, size_t len);
+
+/* ------------------------------------------------------------------------
+ * Batched device entry point (added by this library; north star)
+ * --------------------------------------------------------------------- */
+
+/* One input stream = what a caller would feed to Init(For_All) + Update until
+ * end of input: one or more concatenated modern / legacy / skippable frames. */
+typedef struct lz4ada_batch_item {
+	uint64_t src_off;   /* stream start within the batch source buffer */
+	uint64_t src_len;
+	uint64_t dst_off;   /* where this stream's output goes in the batch output buffer */
+	uint64_t dst_cap;   /* 0 = let the planner place it (packed, 256-byte aligned) */
+} lz4ada_batch_item;
+
+typedef struct lz4ada_batch_result {
+	int32_t  exception;     /* enum lz4ada_exception of the first error in stream order */
+	int32_t  end_of_frame;  /* Is_End_Of_Frame after the last byte */
+	uint32_t n_frames;      /* frames seen (including skippable) */
+	uint32_t n_blocks;
+	uint64_t dst_off;       /* output placement actually used */
+	uint64_t out_len;       /* bytes produced before any error */
+} lz4ada_batch_result;
+
+typedef struct lz4ada_batch lz4ada_batch;
+
+#define LZ4ADA_BATCH_SRC_ON_DEVICE 1u  /* src_dev already holds the compressed bytes */
+
+/* Host stage: parse every frame header and walk the block size words
+ * (lib/lz4ada.adb:155-361, 525-585) to build the block table.  Needs the
+ * compressed bytes in host memory (`src_host`); nothing is decoded here.
+ * ctx may be NULL (the process-wide default context is taken at upload). */
+int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes,
+		uint32_t n_items, const lz4ada_batch_item *items, int reservation,
+		lz4ada_batch **out);
+/* Inspection of the plan (tests, tooling): block `index` of the table in stream order, and
+ * what the host stage alone concluded about stream `item` (header / size-word / Single_Frame
+ * errors, Is_End_Of_Frame at end of input).  Pure host work: usable without a device. */
+int lz4ada_batch_block_desc(const lz4ada_batch *b, uint64_t index, lz4b200_blk_desc *out);
+int lz4ada_batch_host_outcome(const lz4ada_batch *b, uint32_t item, int *exception, int *end_of_frame,
+		uint32_t *n_frames, uint32_t *n_blocks, char *message, size_t message_cap);
+/* Output bytes the plan needs (for allocating the destination). */
+uint64_t lz4ada_batch_output_bytes(const lz4ada_batch *b);
+uint64_t lz4ada_batch_block_count(const lz4ada_batch *b);
+/* Algorithmic traffic of one run: compressed bytes read + bytes written
+ * + bytes re-read for content checksums. */
+void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read,
+		uint64_t *decompressed_written, uint64_t *checksum_reread);
+/* Device stage: upload the tables (and the compressed bytes unless they are
+ * already on the device), run K1..K4, fetch statuses and fold them in stream
+ * order.  src_dev / dst_dev are device pointers sized src_bytes(+32 slack) /
+ * lz4ada_batch_output_bytes(+32 slack).  May be called repeatedly. */
+int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_dev);
+int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev);
+int lz4ada_batch_results(const lz4ada_batch *b, lz4ada_batch_result *results);
+const char *lz4ada_batch_message(const lz4ada_batch *b, uint32_t item);
+void lz4ada_batch_free(lz4ada_batch *b);
+
+/* One call, host buffers in and out: plan + H2D + kernels + D2H.  This is the
+ * end-to-end call bench.py times for `e2e`.  items[k].dst_off / dst_cap are updated with
+ * the placement used; `messages` (optional) receives n_items strings of message_stride bytes. */
+int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes,
+		uint8_t *dst_host, uint64_t dst_bytes, uint32_t n_items,
+		lz4ada_batch_item *items, int reservation, lz4ada_batch_result *results,
+		char *messages, size_t message_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZ4B200_H */

@@ -1,0 +1,472 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI,
+against the CPU oracle and the reference's golden vectors.  Bit-exact: this is byte / integer work.
+Nothing here reads /root/reference."""
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import bo_lz4_ada_b200 as lz
+from tools import corpus
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MAN = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+INLINE = json.load(open(os.path.join(GOLDEN, "inline_cases.json")))
+GOOD = sorted(MAN["good"])
+ERR = sorted(MAN["error"])
+
+
+def _read(name):
+    with open(os.path.join(GOLDEN, name), "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lz.DeviceContext(0)
+    c.make_default()
+    yield c
+    lz.lib().lz4ada_set_device_context(None)
+    c.close()
+
+
+def _check_output(stem, out):
+    e = MAN["good"][stem]
+    assert len(out) == e["size"]
+    assert hashlib.sha256(out).hexdigest() == e["sha256"]
+    if e["bin_in_tree"]:
+        assert out == _read(stem + ".bin")
+
+
+def _drive(dec, data, chunk):
+    """The feeding loop of Test_Good_Case_Inner (test_suite/lz4test.adb:32-83)."""
+    out = bytearray()
+    pos = 0
+    while pos < len(data):
+        end = min(len(data), pos + chunk) if chunk else len(data)
+        while pos < end:
+            c, o, of, ol = dec.Update(data[pos:end])
+            out += o
+            pos += c
+            assert c > 0 or len(o) > 0, "no progress"
+    return bytes(out)
+
+
+# ------------------------------------------------------------------ streaming API (Update)
+
+@pytest.mark.parametrize("stem", GOOD)
+def test_good_case_4k(ctx, stem):
+    """Test_Good_Case_4K (lz4test.adb:254-267) through lz4ada_update: every block decoded on the GPU."""
+    before = ctx.launch_count()
+    dec = lz.Init()
+    out = _drive(dec, _read(stem + ".lz4"), 4096)
+    assert dec.Is_End_Of_Frame() != "No"
+    _check_output(stem, out)
+    if MAN["good"][stem]["size"] > 0:
+        assert ctx.launch_count() > before, "no kernel launched: not the CUDA path"
+
+
+@pytest.mark.parametrize("stem", [s for s in GOOD if MAN["good"][s]["lz4"]["size"] <= 300000])
+def test_good_case_1b(ctx, stem):
+    """Test_Good_Case_1B (lz4test.adb:252, 259-270): one byte per call."""
+    dec = lz.Init()
+    out = _drive(dec, _read(stem + ".lz4"), 1)
+    assert dec.Is_End_Of_Frame() != "No"
+    _check_output(stem, out)
+
+
+def test_update_step_parity_with_oracle(ctx, oracle):
+    """Per-call parity: Num_Consumed, Output_First/Last, the bytes and Is_End_Of_Frame of every
+    Update call equal the oracle's, for awkward chunk sizes."""
+    for stem in ["t300k", "t301k", "concat390", "z101legacyplus", "skipz100", "z2841", "concatlegacy"]:
+        data = _read(stem + ".lz4")
+        for chunk in (1 if len(data) < 2000 else 997, 65536 + 13):
+            a, b = lz.Init(), oracle.init()
+            pos = 0
+            while pos < len(data):
+                piece = data[pos:pos + chunk]
+                ra = a.Update(piece)
+                rb = b.update(piece)
+                assert ra == rb, (stem, chunk, pos)
+                assert a.Is_End_Of_Frame() == b.is_end_of_frame()
+                pos += ra[0]
+
+
+@pytest.mark.parametrize("stem", ERR)
+def test_error_case(ctx, stem):
+    """Test_Error_Case (lz4test.adb:280-351): first 10 001 bytes, Init_With_Header(Single_Frame);
+    Exception_Information must equal the .eds line exactly."""
+    data = _read(stem + ".err")[:10001]
+    with pytest.raises(lz.LZ4AdaError) as ei:
+        dec, total = lz.Init_With_Header(data, "Single_Frame")
+        while total < len(data):
+            c, o, of, ol = dec.Update(data[total:])
+            assert c > 0, "No more data accepted but no exception signalled"
+            total += c
+    assert ei.value.information == MAN["error"][stem]["eds"]
+    assert not isinstance(ei.value, (lz.Device_Error, lz.Constraint_Error, lz.Assertion_Error))
+
+
+def test_decompress_individual_bytes(ctx):
+    """Test_Good_Decompress_Individual_Bytes (lz4test.adb:149-214)."""
+    case = INLINE["two_legacy_frames"]
+    tc = bytes.fromhex(case["input_hex"])
+    dec, consumed0 = lz.Init_With_Header(tc, "For_All")
+    have = b""
+    for i in range(consumed0, len(tc)):
+        consumed = 0
+        while consumed == 0:
+            consumed, out, of, ol = dec.Update(tc[i:i + 1])
+            assert not (consumed == 0 and ol < of)
+            have += out
+    assert have == bytes.fromhex(case["expect_hex"])
+
+
+def test_hello_block(ctx):
+    """Test_Good_Hello_Block (lz4test.adb:216-248)."""
+    case = INLINE["hello_block"]
+    tc = bytes.fromhex(case["input_hex"])
+    dec = lz.Init_For_Block(len(tc))
+    consumed, out, of, ol = dec.Update(tc)
+    assert consumed == len(tc) and dec.Is_End_Of_Frame() == "Yes"
+    assert out == bytes.fromhex(case["expect_hex"]) and of == 0
+
+
+def test_hello_block_in_pieces(ctx):
+    """Raw-block API fed in several chunks (the reference drops 4 cached bytes here, Appendix C)."""
+    tc = bytes.fromhex(INLINE["hello_block"]["input_hex"])
+    dec = lz.Init_For_Block(len(tc))
+    out = b""
+    for i in range(0, len(tc), 5):
+        c, o, _, _ = dec.Update(tc[i:i + 5])
+        assert c == len(tc[i:i + 5])
+        out += o
+    assert out == b"Hello, world."
+
+
+def test_unexpected_multi_frame(ctx):
+    """Test_Error_Case_Unexpected_Multi_Frame (lz4test.adb:384-430)."""
+    tc = bytes.fromhex(INLINE["unexpected_multi_frame"]["input_hex"])
+    dec, total = lz.Init_With_Header(tc, "Single_Frame")
+    with pytest.raises(lz.Data_Corruption) as ei:
+        while total < len(tc):
+            c, o, of, ol = dec.Update(tc[total:])
+            total += c
+    assert "looks like the beginning of another frame" in str(ei.value)
+
+
+# ------------------------------------------------------------------ batched entry point
+
+def test_batch_all_good_vectors(ctx):
+    """All 24 good vectors as one batch: K1 (independent), K4 (linked: t300k/t301k/z2841/b3444k),
+    K5 pre-sizing (concatenated frames), K3 content checksums."""
+    streams = [_read(s + ".lz4") for s in GOOD]
+    before = ctx.launch_count()
+    res = lz.batch_decompress(ctx, streams)
+    assert ctx.launch_count() - before >= 3
+    for stem, (exc, out, eof, msg) in zip(GOOD, res):
+        assert exc == "OK", (stem, msg)
+        assert eof != "No", stem
+        _check_output(stem, out)
+
+
+def test_batch_error_vectors_match_oracle(ctx, oracle):
+    """Every .err vector through the batch path (Init(For_All) semantics) = the oracle's
+    Init(For_All)+Update loop: same exception, same text, same bytes before the error."""
+    streams = [_read(s + ".err") for s in ERR]
+    res = lz.batch_decompress(ctx, streams)
+    for stem, data, (exc, out, eof, msg) in zip(ERR, streams, res):
+        oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 22)
+        assert (exc, msg) == (oexc, omsg), stem
+        assert out == oout, stem
+
+
+def _synthetic_frames():
+    rng = np.random.default_rng(11)
+    text = corpus.text_like(700000, seed=3)
+    rle = corpus.rle_like(600000, seed=4)
+    rnd = corpus.random_bytes(200000, seed=5)
+    mix = text[:150000] + rnd[:70000] + rle[:150000] + text[150000:300000]
+    cases = []
+    for code in (4, 5, 6, 7):
+        for indep in (True, False):
+            for bchk in (True, False):
+                cases.append(("mix-b%d-%s-%s" % (code, "i" if indep else "l", "bc" if bchk else "nb"),
+                              corpus.build_frame(mix, code, bchk, True, True, indep), mix))
+    cases.append(("text-64k", corpus.build_frame(text, 4, True, True), text))
+    cases.append(("rle-4m", corpus.build_frame(rle, 7, False, True), rle))
+    cases.append(("random-stored", corpus.build_frame(rnd, 4, True, True), rnd))
+    cases.append(("legacy", corpus.build_legacy_frame(text + rle, block_size=1 << 20), text + rle))
+    cases.append(("greedy-enc", corpus.build_frame(text, 5, True, True, encoder="greedy"), text))
+    cases.append(("short-interior-blocks", corpus.build_frame(text[:300000], 4, False, True, block_size=50000),
+                  text[:300000]))
+    cases.append(("linked-short-blocks", corpus.build_frame(text[:300000], 4, True, True, independent=False,
+                                                            block_size=30000), text[:300000]))
+    cases.append(("dict-id-field", corpus.build_frame(text[:5000], 4, False, True, dict_id=7), text[:5000]))
+    cases.append(("concat+skip", corpus.skippable_frame(b"x" * 33, 3) + corpus.build_frame(text[:70000], 4) +
+                  corpus.build_frame(rle[:99999], 4, True) + corpus.skippable_frame(b"", 15) +
+                  corpus.build_frame(b"", 4), text[:70000] + rle[:99999]))
+    # tiny inputs and every small period
+    for n in (1, 2, 3, 4, 5, 12, 13, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 1000):
+        d = bytes(rng.integers(97, 100, n, dtype=np.uint8))
+        cases.append(("tiny-%d" % n, corpus.build_frame(d, 4, True, True, True), d))
+    for period in list(range(1, 41)) + [63, 64, 65, 100, 511, 512, 513, 4000]:
+        pat = bytes(rng.integers(0, 256, period, dtype=np.uint8))
+        d = (pat * (70000 // period + 2))[:70000 - period % 7]
+        cases.append(("period-%d" % period, corpus.build_frame(d, 4, False, True), d))
+    return cases
+
+
+def test_batch_synthetic_vs_oracle_and_plain(ctx, oracle):
+    cases = _synthetic_frames()
+    res = lz.batch_decompress(ctx, [c[1] for c in cases])
+    for (name, frame, plain), (exc, out, eof, msg) in zip(cases, res):
+        assert exc == "OK", (name, msg)
+        assert out == plain, name
+        oexc, oout, oeof, omsg = oracle.decode_stream(frame, chunk=65536, out_cap=len(plain) + 64)
+        assert (oexc, oout, oeof) == ("OK", plain, eof), name
+
+
+def test_streaming_synthetic(ctx):
+    """A few synthetic frames through Update as well (device-resident history across linked blocks)."""
+    for name, frame, plain in _synthetic_frames()[:8] + _synthetic_frames()[16:24]:
+        dec = lz.Init()
+        assert _drive(dec, frame, 100000) == plain, name
+
+
+def _mutations(frame, rng, n):
+    out = []
+    for _ in range(n):
+        b = bytearray(frame)
+        kind = rng.integers(0, 4)
+        if kind == 0:      # flip a byte after the header
+            i = int(rng.integers(7, len(b)))
+            b[i] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:    # overwrite a few bytes
+            i = int(rng.integers(7, len(b) - 4))
+            b[i:i + 3] = bytes(rng.integers(0, 256, 3, dtype=np.uint8))
+        elif kind == 2:    # truncate
+            b = b[:int(rng.integers(1, len(b)))]
+        else:              # 0xff burst (length-extension stress)
+            i = int(rng.integers(7, len(b) - 8))
+            b[i:i + 6] = b"\xff" * 6
+        out.append(bytes(b))
+    return out
+
+
+def test_fuzz_error_parity_with_oracle(ctx, oracle):
+    """Corrupted streams: the batch path and the oracle must report the same first exception with
+    the same text and the same output before it (SURVEY.md Appendix A ordering).  Frames without
+    block checksums so that the corruption reaches the sequence decoder."""
+    rng = np.random.default_rng(2024)
+    text = corpus.text_like(40000, seed=9)
+    mix = text[:9000] + bytes(3000) + text[9000:14000]
+    bases = [corpus.build_frame(mix, 4, False, True, True), corpus.build_frame(mix, 4, True, False, False),
+             corpus.build_frame(text, 4, False, False, False, independent=False, block_size=9000),
+             corpus.build_legacy_frame(mix), _read("t100k.lz4")[:30000]]
+    streams = []
+    for base in bases:
+        streams += _mutations(base, rng, 60)
+    res = lz.batch_decompress(ctx, streams)
+    kinds = {}
+    for k, (data, (exc, out, eof, msg)) in enumerate(zip(streams, res)):
+        oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 21)
+        assert (exc, msg) == (oexc, omsg), (k, exc, msg, oexc, omsg)
+        assert out == oout, k
+        if exc == "OK":
+            assert eof == oeof, k
+        kinds[msg.split(" : ")[1][:28] if msg else "OK"] = kinds.get(msg[:1], 0) + 1
+    assert len(kinds) >= 5, kinds    # the fuzz actually reached several distinct raise sites
+
+
+def test_fuzz_streaming_error_parity(ctx, oracle):
+    """Same idea through Update (Init(For_All), 4 KiB chunks)."""
+    rng = np.random.default_rng(77)
+    text = corpus.text_like(30000, seed=10)
+    base = corpus.build_frame(text, 4, False, True, True, independent=False, block_size=7000)
+    for data in _mutations(base, rng, 40):
+        oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=4096, out_cap=1 << 21)
+        dec = lz.Init()
+        out = bytearray()
+        exc, msg = "OK", ""
+        try:
+            pos = 0
+            while pos < len(data):
+                end = min(len(data), pos + 4096)
+                idle = 0
+                while pos < end:
+                    c, o, of, ol = dec.Update(data[pos:end])
+                    out += o
+                    pos += c
+                    idle = idle + 1 if (c == 0 and not o) else 0
+                    assert idle < 5
+        except lz.LZ4AdaError as e:
+            exc, msg = e.ada_name, e.information
+        assert (exc, msg) == (oexc, omsg)
+        assert bytes(out) == oout
+
+
+# ------------------------------------------------------------------ kernels through the shim
+
+def test_k3_xxh32_spans_alignment_and_lengths(ctx, oracle):
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 1 << 20, dtype=np.uint8).tobytes()
+    spans = []
+    for n in [0, 1, 3, 4, 15, 16, 17, 31, 32, 33, 47, 48, 127, 128, 129, 1000, 4096, 65536, 300001]:
+        for mis in (0, 1, 2, 3, 5, 16):
+            spans.append((1000 + mis, n))
+    arr = (lz.HashSpan * len(spans))(*[lz.HashSpan(o, n) for o, n in spans])
+    d_data = ctx.alloc(len(data))
+    d_spans = ctx.alloc(ctypes_sizeof(arr))
+    d_out = ctx.alloc(4 * len(spans))
+    ctx.h2d(d_data, data)
+    ctx.h2d(d_spans, bytes(arr))
+    rc = lz.lib().lz4b200_xxh32_spans(ctx.handle, d_data, len(spans), d_spans, d_out)
+    assert rc == 0
+    got = struct.unpack("<%dI" % len(spans), ctx.d2h(d_out, 4 * len(spans)))
+    for (o, n), g in zip(spans, got):
+        assert g == oracle.xxh32(data[o:o + n]), (o, n)
+    for p in (d_data, d_spans, d_out):
+        ctx.free(p)
+
+
+def ctypes_sizeof(a):
+    import ctypes
+    return ctypes.sizeof(a)
+
+
+def _raw_block(seqs, last_literals=b""):
+    """Hand-assembled LZ4 block from (literals, offset, match_len) triples."""
+    out = bytearray()
+    for lit, off, ml in seqs:
+        ll, mm = len(lit), ml - 4
+        out.append((min(ll, 15) << 4) | min(mm, 15))
+        if ll >= 15:
+            r = ll - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+        out += lit
+        out += struct.pack("<H", off)
+        if mm >= 15:
+            r = mm - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+    ll = len(last_literals)
+    out.append(min(ll, 15) << 4)
+    if ll >= 15:
+        r = ll - 15
+        while r >= 255:
+            out.append(255)
+            r -= 255
+        out.append(r)
+    out += last_literals
+    return bytes(out)
+
+
+def _py_decode(block):
+    """Tiny pure-Python LZ4 block decoder (test-side cross-check, small cases only)."""
+    out = bytearray()
+    i = 0
+    while i < len(block):
+        t = block[i]; i += 1
+        ll = t >> 4
+        if ll == 15:
+            while True:
+                b = block[i]; i += 1; ll += b
+                if b != 255:
+                    break
+        out += block[i:i + ll]; i += ll
+        if i >= len(block):
+            break
+        off = block[i] | (block[i + 1] << 8); i += 2
+        ml = t & 15
+        if ml == 15:
+            while True:
+                b = block[i]; i += 1; ml += b
+                if b != 255:
+                    break
+        ml += 4
+        for _ in range(ml):
+            out.append(out[-off])
+    return bytes(out)
+
+
+def test_k1_overlap_matrix_direct(ctx, oracle):
+    """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
+    warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
+    rng = np.random.default_rng(8)
+    blocks, expect = [], []
+    for off in list(range(1, 71)) + [255, 256, 257, 511, 512, 513, 1000]:
+        for ml in (4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 200, 513, 2000, 70000):
+            lead = bytes(rng.integers(0, 256, max(off, 1) + int(rng.integers(0, 9)), dtype=np.uint8))
+            blk = _raw_block([(lead, off, ml)], b"tail!")
+            blocks.append(blk)
+            exp = bytearray(lead)
+            if ml <= 2000:
+                for _ in range(ml):
+                    exp.append(exp[-off])
+            else:
+                base = bytes(exp[-off:])
+                exp += (base * (ml // off + 2))[:ml]
+            expect.append(bytes(exp) + b"tail!")
+    cap = 80000
+    src = b"".join(blocks)
+    descs = (lz.BlkDesc * len(blocks))()
+    pos = 0
+    for i, blk in enumerate(blocks):
+        descs[i].src_off, descs[i].src_len = pos, len(blk)
+        descs[i].dst_off, descs[i].dst_cap = i * cap + (i % 16), cap - 16
+        descs[i].flags, descs[i].hist_avail = 0, 0
+        pos += len(blk)
+    d_src, d_dst = ctx.alloc(len(src)), ctx.alloc(cap * len(blocks))
+    d_desc, d_st = ctx.alloc(ctypes_sizeof(descs)), ctx.alloc(24 * len(blocks))
+    ctx.h2d(d_src, src)
+    ctx.h2d(d_desc, bytes(descs))
+    assert lz.lib().lz4b200_decode_blocks(ctx.handle, d_src, d_dst, len(blocks), d_desc, d_st) == 0
+    st = ctx.d2h(d_st, 24 * len(blocks))
+    out = ctx.d2h(d_dst, cap * len(blocks))
+    for i, exp in enumerate(expect):
+        code, out_len = struct.unpack_from("<II", st, 24 * i)
+        assert code == 0 and out_len == len(exp), (i, code, out_len, len(exp))
+        o = descs[i].dst_off
+        assert out[o:o + out_len] == exp, i
+    for p in (d_src, d_dst, d_desc, d_st):
+        ctx.free(p)
+
+
+def test_py_decoder_agrees_on_vector(oracle):
+    """Sanity of the test-side helper against a golden vector (keeps _py_decode honest)."""
+    frame = _read("z100.lz4")
+    assert _py_decode(frame[11:11 + 11]) == _read("z100.bin")
+
+
+def test_property_roundtrip_large(ctx):
+    """Size-independent property at a larger size than the oracle is run on: encode -> GPU decode
+    -> byte compare, plus the device content checksum agreeing with the encoder's (a checksum of
+    checksums over 64 frames x 1 MiB, 64 KiB blocks, block + content checksums)."""
+    c = corpus.build_corpus(64 << 20, 1 << 20, 4, kinds=("text", "rle", "random"), keep_plain=True)
+    b = lz.Batch(ctx, c["src"], c["items"])
+    d_src, d_dst = ctx.alloc(len(c["src"])), ctx.alloc(b.output_bytes)
+    b.upload(d_src)
+    b.run(d_src, d_dst)
+    total = 0
+    for r, plain in zip(b.results(), c["plain"]):
+        assert r["exception"] == "OK", r
+        assert r["out_len"] == len(plain)
+        assert ctx.d2h(d_dst + r["dst_off"], r["out_len"]) == plain
+        total += r["out_len"]
+    t = b.traffic()
+    assert t["decompressed_written"] == total == t["checksum_reread"]
+    b.close()
+    ctx.free(d_src)
+    ctx.free(d_dst)
