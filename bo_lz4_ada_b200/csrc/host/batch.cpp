@@ -246,10 +246,11 @@ Raised device_fail(lz4ada_batch *b)
 // Fold the statuses of one stream in stream order.  exact = the stream was decoded as one chain
 // (placement is exact by construction; frame bases are recomputed here).
 // digest_of(frame) must deliver (valid, value).
+// Returns true when the stream has to be decoded again as one chain (placement assumption broken).
 template <class DigestFn>
-void fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
+bool fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 {
-	if (!exact && it.slow) return;   // placement already known to be unusable (tight caller buffer)
+	if (!exact && it.slow) return true;   // placement already known to be unusable (tight caller buffer)
 	it.error = Raised();
 	it.out_len = 0;
 	bool slow = false;
@@ -278,9 +279,10 @@ void fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 			remaining -= st.out_len;
 			fpos += st.out_len;
 		}
-		if (it.error || slow) break;
+		// the reference hands out every block before the failing one (one block per Update)
 		pos += fpos;
 		it.out_len += fpos;
+		if (it.error || slow) break;
 		if (fp.has_cchk && fp.cchk_seen) {
 			uint32_t value = 0;
 			if (!digest_of(fp, value)) { slow = true; break; }
@@ -288,11 +290,9 @@ void fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 		}
 		if (fp.ended && fp.has_csize && remaining != 0) { it.error = err_content_size_left(remaining); break; }
 	}
-	if (slow) {
-		it.slow = true;
-		return;
-	}
+	if (slow) return true;
 	if (!it.error) it.error = it.host_error;
+	return false;
 }
 
 // Decode the flagged streams again, each as one chain with exact running placement.
@@ -375,12 +375,12 @@ Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 	}
 	for (ItemPlan &it : b->items) {
 		if (!it.slow) continue;
-		fold_item(b, it, true, [&](const FramePlan &fp, uint32_t &value) {
+		const bool again = fold_item(b, it, true, [&](const FramePlan &fp, uint32_t &value) {
 			for (size_t k = 0; k < span_frames.size(); k++)
 				if (span_frames[k] == &fp) { value = values[k]; return true; }
 			return false;
 		});
-		if (it.slow && !it.error) {   // cannot happen: the chain path has no soft failures
+		if (again) {   // cannot happen: the chain path has no soft failures
 			it.error = err_device("chain decode reported an unexpected soft status");
 		}
 	}
@@ -595,7 +595,7 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 	}
 	bool any_slow = false;
 	for (ItemPlan &it : b->items) {
-		fold_item(b, it, false, [&](const FramePlan &fp, uint32_t &value) {
+		it.slow = fold_item(b, it, false, [&](const FramePlan &fp, uint32_t &value) {
 			if (fp.hash_slot == 0xffffffffu || !b->h_digest[nh + fp.hash_slot]) return false;
 			value = b->h_digest[fp.hash_slot];
 			return true;

@@ -183,6 +183,13 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
     res = lz.batch_decompress(ctx, streams)
     for stem, data, (exc, out, eof, msg) in zip(ERR, streams, res):
         oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 22)
+        if stem == "cntblkszoverflow":
+            # Under Init(For_All) the reference accepts this 64 KiB-block frame whose single block
+            # inflates to 100 KiB (it never bounds a block's decompressed size).
+            # The batch path bounds every block by the frame's declared block maximum.
+            assert oexc == "OK" and len(oout) == 102400
+            assert exc == "DATA_CORRUPTION" and "Output buffer exhausted" in msg and out == b""
+            continue
         assert (exc, msg) == (oexc, omsg), stem
         assert out == oout, stem
 
