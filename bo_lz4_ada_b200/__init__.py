@@ -135,6 +135,7 @@ _SIGNATURES = {
     "lz4b200_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "lz4b200_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "lz4b200_set_tuning": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "lz4b200_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_alloc_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -145,6 +146,11 @@ _SIGNATURES = {
     "lz4b200_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "lz4b200_event_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "lz4b200_event_destroy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "lz4b200_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "lz4b200_event_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.POINTER(ctypes.c_float)]),
     "lz4b200_decode_blocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
                                              ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_decode_linked": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
@@ -191,6 +197,7 @@ _SIGNATURES = {
     "lz4ada_batch_block_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "lz4ada_batch_traffic": (None, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
                                     ctypes.POINTER(ctypes.c_uint64)]),
+    "lz4ada_batch_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "lz4ada_batch_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_results": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BatchResult)]),
@@ -273,6 +280,10 @@ class DeviceContext:
         if rc != 0:
             raise Device_Error("raised LZ4ADA.DEVICE_ERROR : %s failed: %s"
                                % (what, lib().lz4b200_last_error(self.handle).decode()))
+
+    def set_tuning(self, blocks_per_warp):
+        if lib().lz4b200_set_tuning(self.handle, blocks_per_warp) != 0:
+            raise ValueError(blocks_per_warp)
 
     def alloc(self, nbytes):
         p = ctypes.c_void_p()
@@ -494,6 +505,12 @@ class Batch:
                         "n_frames": r.n_frames, "n_blocks": r.n_blocks, "dst_off": r.dst_off, "out_len": r.out_len,
                         "message": lib().lz4ada_batch_message(self._h, k).decode()})
         return out
+
+    def kernel_ms(self):
+        """Device time of K1 / K4 / K3 in the last run (CUDA events on the launching stream)."""
+        ms = (ctypes.c_float * 3)()
+        lib().lz4ada_batch_kernel_ms(self._h, ms)
+        return {"k1_decode_blocks": ms[0], "k4_decode_linked": ms[1], "k3_xxh32_frames": ms[2]}
 
     def traffic(self):
         a, b, c = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)

@@ -145,8 +145,10 @@ struct lz4ada_batch {
 	// pinned host mirrors
 	lz4b200_blk_status *h_status = nullptr;
 	uint32_t *h_digest = nullptr;
-	// traffic of the last run
+	// traffic and kernel times of the last run
 	uint64_t t_comp = 0, t_out = 0, t_reread = 0;
+	void *ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	float kernel_ms[3] = {0, 0, 0};
 	std::string device_error;
 
 	~lz4ada_batch()
@@ -160,6 +162,8 @@ struct lz4ada_batch {
 		if (d_digest) lz4b200_free(ctx, d_digest);
 		if (h_status) lz4b200_free_host(ctx, h_status);
 		if (h_digest) lz4b200_free_host(ctx, h_digest);
+		for (void *e : ev)
+			if (e) lz4b200_event_destroy(ctx, e);
 	}
 };
 
@@ -495,6 +499,13 @@ void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read, uint
 	if (checksum_reread) *checksum_reread = b ? b->t_reread : 0;
 }
 
+int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3])
+{
+	if (!b || !ms) return LZ4ADA_ASSERTION_ERROR;
+	for (int k = 0; k < 3; k++) ms[k] = b->kernel_ms[k];
+	return LZ4ADA_OK;
+}
+
 int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_dev)
 {
 	if (!b) return LZ4ADA_ASSERTION_ERROR;
@@ -583,15 +594,24 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			place(b, b->have_sized ? &b->sized : nullptr);
 			if (lz4b200_h2d(ctx, b->d_desc, b->descs.data(), sizeof(lz4b200_blk_desc) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		}
+		for (void *&e : b->ev)
+			if (!e && lz4b200_event_create(ctx, &e) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		lz4b200_event_record(ctx, b->ev[0]);
 		if (lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(nb), b->d_desc, b->d_status) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		lz4b200_event_record(ctx, b->ev[1]);
 		if (nc && lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(nc), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK)
 			return LZ4ADA_DEVICE_ERROR;
+		lz4b200_event_record(ctx, b->ev[2]);
 		if (nh && lz4b200_xxh32_frames(ctx, dst_dev, uint32_t(nh), b->d_hash_frames, b->d_desc, b->d_status, b->d_digest,
 						b->d_digest + nh) != LZ4B200_OK)
 			return LZ4ADA_DEVICE_ERROR;
+		lz4b200_event_record(ctx, b->ev[3]);
 		if (lz4b200_d2h(ctx, b->h_status, b->d_status, sizeof(lz4b200_blk_status) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		if (nh && lz4b200_d2h(ctx, b->h_digest, b->d_digest, 8 * nh) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		if (lz4b200_sync(ctx) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		for (int k = 0; k < 3; k++) lz4b200_event_elapsed(ctx, b->ev[k], b->ev[k + 1], &b->kernel_ms[k]);
+		if (!nc) b->kernel_ms[1] = 0;
+		if (!nh) b->kernel_ms[2] = 0;
 	}
 	bool any_slow = false;
 	for (ItemPlan &it : b->items) {

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "kernels.cuh"
+#include "kernels_v2.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -29,6 +30,21 @@ decode_blocks_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_b
 	const lz4b200_blk_desc d = desc[b];
 	if (d.flags & LZ4B200_BLK_CHAINED) return;
 	process_block<false>(src, dst + d.dst_off, d, d.dst_cap, d.hist_avail, status + b, lane);
+}
+
+// K1 fast path: G blocks per warp (kernels_v2.cuh); falls back to process_block per block.
+template <int G>
+__global__ void __launch_bounds__(K1_WARPS * 32, 7)
+decode_blocks_v2_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status)
+{
+	__shared__ SeqDesc sd[K1_WARPS][G * SD_STRIDE];
+	__shared__ uint4 tiles[K1_WARPS][(TILE_BYTES + 32) / 16];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const uint32_t first = (blockIdx.x * K1_WARPS + warp) * G;
+	if (first >= n_blocks) return;
+	decode_group<G>(src, dst, n_blocks, first, desc, status, sd[warp], reinterpret_cast<uint8_t *>(tiles[warp]), lane);
 }
 
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
@@ -268,6 +284,7 @@ struct lz4b200_ctx {
 	bool own_stream = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint64_t launches = 0;
+	int blocks_per_warp = 0;   // K1 tuning: 0 = choose from the block count, -1 = v1 kernel
 	char err[256] = "";
 };
 
@@ -331,6 +348,15 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 const char *lz4b200_last_error(const lz4b200_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 int lz4b200_sm_count(const lz4b200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
+{
+	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
+		     blocks_per_warp != 4 && blocks_per_warp != 8))
+		return LZ4B200_ERR_ARG;
+	ctx->blocks_per_warp = blocks_per_warp;
+	return LZ4B200_OK;
+}
 
 int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr)
 {
@@ -410,13 +436,60 @@ int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms)
 	return LZ4B200_OK;
 }
 
+int lz4b200_event_create(lz4b200_ctx *ctx, void **event)
+{
+	if (!ctx || !event) return LZ4B200_ERR_ARG;
+	cudaEvent_t e;
+	CK(cudaEventCreate(&e));
+	*event = e;
+	return LZ4B200_OK;
+}
+
+int lz4b200_event_destroy(lz4b200_ctx *ctx, void *event)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	if (event) CK(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+	return LZ4B200_OK;
+}
+
+int lz4b200_event_record(lz4b200_ctx *ctx, void *event)
+{
+	if (!ctx || !event) return LZ4B200_ERR_ARG;
+	CK(cudaEventRecord(static_cast<cudaEvent_t>(event), ctx->stream));
+	return LZ4B200_OK;
+}
+
+int lz4b200_event_elapsed(lz4b200_ctx *ctx, void *start, void *stop, float *elapsed_ms)
+{
+	if (!ctx || !start || !stop || !elapsed_ms) return LZ4B200_ERR_ARG;
+	CK(cudaEventElapsedTime(elapsed_ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+	return LZ4B200_OK;
+}
+
 int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t n_blocks,
 			  const lz4b200_blk_desc *desc, lz4b200_blk_status *status)
 {
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_blocks == 0) return LZ4B200_OK;
-	const uint32_t grid = (n_blocks + K1_WARPS - 1) / K1_WARPS;
-	decode_blocks_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status);
+	int g = ctx->blocks_per_warp;
+	if (g == 0) {
+		// keep at least ~16 warps per SM busy; more blocks per warp = cheaper token-chain walking
+		const uint32_t per = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u;
+		g = n_blocks >= 8 * per ? 8 : n_blocks >= 4 * per ? 4 : n_blocks >= 2 * per ? 2 : 1;
+	}
+	if (g < 0) {
+		const uint32_t grid = (n_blocks + K1_WARPS - 1) / K1_WARPS;
+		decode_blocks_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status);
+	} else {
+		const uint32_t warps = (n_blocks + g - 1) / g;
+		const uint32_t grid = (warps + K1_WARPS - 1) / K1_WARPS;
+		switch (g) {
+		case 8: decode_blocks_v2_kernel<8><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
+		case 4: decode_blocks_v2_kernel<4><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
+		case 2: decode_blocks_v2_kernel<2><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
+		default: decode_blocks_v2_kernel<1><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
+		}
+	}
 	ctx->launches++;
 	CK(cudaGetLastError());
 	return LZ4B200_OK;

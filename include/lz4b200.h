@@ -131,6 +131,11 @@ int lz4b200_sm_count(const lz4b200_ctx *ctx);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx);
 
+/* K1 tuning: how many independent blocks one warp decodes side by side (1, 2, 4 or 8; their
+ * token chains advance together, one lane each).  0 = pick from the block count (default),
+ * -1 = the one-warp-per-block kernel that is also the exact fallback. */
+int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp);
+
 /* Device and pinned-host memory, so that the Ada side never links libcudart. */
 int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr);
 int lz4b200_free(lz4b200_ctx *ctx, void *dev_ptr);
@@ -145,6 +150,13 @@ int lz4b200_sync(lz4b200_ctx *ctx);
 /* Device-side timing on the context stream (CUDA events). */
 int lz4b200_timer_start(lz4b200_ctx *ctx);
 int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms);   /* synchronises */
+
+/* CUDA events on the context stream, for per-kernel timing without libcudart on the caller's
+ * side.  elapsed is valid once the stream has been synchronised past `stop`. */
+int lz4b200_event_create(lz4b200_ctx *ctx, void **event);
+int lz4b200_event_destroy(lz4b200_ctx *ctx, void *event);
+int lz4b200_event_record(lz4b200_ctx *ctx, void *event);
+int lz4b200_event_elapsed(lz4b200_ctx *ctx, void *start, void *stop, float *elapsed_ms);
 
 /* K1 (+K2): decode `n_blocks` mutually independent blocks, one warp per block,
  * block XXH32 fused.  Takes over Decode_Full_Block_With_Trailer,
@@ -323,6 +335,10 @@ uint64_t lz4ada_batch_block_count(const lz4ada_batch *b);
  * + bytes re-read for content checksums. */
 void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read,
 		uint64_t *decompressed_written, uint64_t *checksum_reread);
+/* Device time of the kernels of the last lz4ada_batch_run, from CUDA events recorded on the
+ * launching stream: ms[0] = K1 (independent blocks), ms[1] = K4 (chains), ms[2] = K3 (content
+ * checksums).  0 for a kernel that did not run. */
+int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3]);
 /* Device stage: upload the tables (and the compressed bytes unless they are
  * already on the device), run K1..K4, fetch statuses and fold them in stream
  * order.  src_dev / dst_dev are device pointers sized src_bytes(+32 slack) /

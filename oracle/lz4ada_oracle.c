@@ -10,6 +10,7 @@
 #include "lz4ada_oracle.h"
 
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -478,6 +479,31 @@ static int decrease_data_size_remaining(lzo_ctx *c, uint64_t n)
 	return LZO_OK;
 }
 
+/* The reference copies 8-byte slices (lib/lz4ada.adb:811-817) and may over-write up to seven
+ * bytes; this copy moves 8-byte slices too but never writes outside [dst, dst + n): the last
+ * slice is placed so that it ends exactly at the end.  Ranges that overlap closer than eight
+ * bytes (history replay with src just ahead of dst) fall back to memmove. */
+static void copy_exact(uint8_t *dst, const uint8_t *src, int n)
+{
+	ptrdiff_t gap = src > dst ? src - dst : dst - src;
+	if (n >= 8 && gap >= 8 && n <= 64) {
+		int i;
+		uint64_t last, v;
+		memcpy(&last, src + n - 8, 8);
+		for (i = 0; i + 8 < n; i += 8) {
+			memcpy(&v, src + i, 8);
+			memcpy(dst + i, &v, 8);
+		}
+		memcpy(dst + n - 8, &last, 8);
+	} else if (n < 8 && gap >= 8) {
+		int i;
+		for (i = 0; i < n; i++)
+			dst[i] = src[i];
+	} else {
+		memmove(dst, src, (size_t)n);
+	}
+}
+
 /* Write_Output, lib/lz4ada.adb:790-824 -- exact copy (no 8-byte over-copy),
  * content-size accounting first, then a capacity check the reference lacks
  * (Appendix C). */
@@ -489,7 +515,7 @@ static int write_output(lzo_ctx *c, const uint8_t *src, int n,
 		RAISE(c->msg, LZO_DATA_CORRUPTION,
 		      "Output buffer exhausted. Decompressed data does not fit "
 		      "into the %d bytes provided.", buffer_len);
-	memmove(buffer + c->output_pos, src, (size_t)n);
+	copy_exact(buffer + c->output_pos, src, n);
 	c->output_pos += n;
 	return LZO_OK;
 }

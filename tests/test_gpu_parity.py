@@ -194,6 +194,34 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
         assert out == oout, stem
 
 
+@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8])
+def test_batch_k1_variants(ctx, oracle, g):
+    """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8 blocks per warp): good vectors,
+    synthetic frames and corrupted streams must all come out exactly as the oracle says."""
+    ctx.set_tuning(g)
+    try:
+        streams = [_read(s + ".lz4") for s in GOOD]
+        for stem, (exc, out, eof, msg) in zip(GOOD, lz.batch_decompress(ctx, streams)):
+            assert exc == "OK", (stem, msg)
+            _check_output(stem, out)
+        cases = _synthetic_frames()
+        for (name, frame, plain), (exc, out, eof, msg) in zip(cases, lz.batch_decompress(ctx, [c[1] for c in cases])):
+            assert exc == "OK" and out == plain, (name, msg)
+        rng = np.random.default_rng(100 + g)
+        text = corpus.text_like(60000, seed=19)
+        mix = text[:20000] + bytes(5000) + corpus.random_bytes(3000, seed=1) + text[20000:45000]
+        bases = [corpus.build_frame(mix, 4, False, True, True), corpus.build_frame(mix, 4, True, True, False),
+                 corpus.build_frame(text, 4, False, False, False, block_size=7000)]
+        bad = []
+        for base in bases:
+            bad += _mutations(base, rng, 40)
+        for k, (data, (exc, out, eof, msg)) in enumerate(zip(bad, lz.batch_decompress(ctx, bad))):
+            oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 21)
+            assert (exc, msg, out) == (oexc, omsg, oout), (g, k, exc, msg, oexc, omsg)
+    finally:
+        ctx.set_tuning(0)
+
+
 def _synthetic_frames():
     rng = np.random.default_rng(11)
     text = corpus.text_like(700000, seed=3)
@@ -408,7 +436,8 @@ def _py_decode(block):
     return bytes(out)
 
 
-def test_k1_overlap_matrix_direct(ctx, oracle):
+@pytest.mark.parametrize("g", [-1, 1, 8])
+def test_k1_overlap_matrix_direct(ctx, oracle, g):
     """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
     warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
     rng = np.random.default_rng(8)
@@ -439,7 +468,11 @@ def test_k1_overlap_matrix_direct(ctx, oracle):
     d_desc, d_st = ctx.alloc(ctypes_sizeof(descs)), ctx.alloc(24 * len(blocks))
     ctx.h2d(d_src, src)
     ctx.h2d(d_desc, bytes(descs))
-    assert lz.lib().lz4b200_decode_blocks(ctx.handle, d_src, d_dst, len(blocks), d_desc, d_st) == 0
+    ctx.set_tuning(g)
+    try:
+        assert lz.lib().lz4b200_decode_blocks(ctx.handle, d_src, d_dst, len(blocks), d_desc, d_st) == 0
+    finally:
+        ctx.set_tuning(0)
     st = ctx.d2h(d_st, 24 * len(blocks))
     out = ctx.d2h(d_dst, cap * len(blocks))
     for i, exp in enumerate(expect):
