@@ -161,6 +161,95 @@ __device__ __forceinline__ uint32_t quad_xxh32(const uint8_t *p, uint64_t n, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Long spans (content checksums): the chain needs 16 bytes every ~14 cycles per frame, but a frame
+// only has four lanes, so register-staged loads keep far too few bytes in flight (measured 1.3 TB/s
+// with 4096 chains).  Here each quad streams its span through a 2 KiB shared-memory ring filled by
+// cp.async (LDGSTS, 16 bytes per lane, eight 256-byte groups in flight per quad = 8 MB in flight
+// for 4096 frames) and folds stripes straight out of shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t XXH_RING_BYTES = 2048;            // per quad
+constexpr uint32_t XXH_GROUP_BYTES = 256;            // 4 x (4 lanes x 16 B)
+constexpr uint32_t XXH_GROUPS = XXH_RING_BYTES / XXH_GROUP_BYTES;
+constexpr uint32_t XXH_RING_STRIDE = XXH_RING_BYTES + 16;   // 16-byte skew per quad: conflict-free LDS
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// All 32 lanes call this together; ring = this warp's 8 x XXH_RING_STRIDE bytes of shared memory.
+__device__ __forceinline__ uint32_t quad_xxh32_stream(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
+{
+	const int sub = lane & 3, q = lane >> 2;
+	uint8_t *my_ring = ring + q * XXH_RING_STRIDE;
+	const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(my_ring);
+	const uint64_t nstripes = n >> 4;
+	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+	const uint32_t mis = static_cast<uint32_t>(a & 15);
+	const uint8_t *abase = p - mis;                                   // 16-byte aligned
+	const uint64_t need = nstripes ? mis + (nstripes << 4) + 4 : 0;    // bytes from abase the stripes touch
+	const uint32_t my_groups = static_cast<uint32_t>((need + XXH_GROUP_BYTES - 1) / XXH_GROUP_BYTES);
+	const uint32_t max_groups = __reduce_max_sync(FULL_MASK, my_groups);
+	const uint32_t sh = (mis & 3) * 8;
+	uint32_t acc = xxh_init_acc(sub);
+
+	auto issue = [&](uint32_t g) {
+		if (g < my_groups) {
+			const uint64_t gb = static_cast<uint64_t>(g) * XXH_GROUP_BYTES;
+			uint8_t *slot = my_ring + (gb & (XXH_RING_BYTES - 1));
+#pragma unroll
+			for (int c = 0; c < 4; c++) cp_async16(slot + c * 64 + sub * 16, abase + gb + c * 64 + sub * 16);
+		}
+		cp_async_commit();
+	};
+	for (uint32_t g = 0; g < XXH_GROUPS; g++) issue(g);
+	// Iteration g runs once group g has landed and folds stripe batch g - 1 (16 stripes = 256 bytes):
+	// lagging by one group means the bytes a misaligned span spills into the next group are there.
+	const uint64_t n_batches = (nstripes + 15) >> 4;
+	constexpr uint32_t WMASK = XXH_RING_BYTES / 4 - 1;
+	for (uint32_t g = 0; g <= max_groups; g++) {
+		// commits so far: 8 (prologue) + (g - 1); all but the newest 6 are complete => groups 0..g landed
+		cp_async_wait<XXH_GROUPS - 2>();
+		__syncwarp();
+		if (g >= 1 && g - 1 < n_batches) {
+			const uint64_t s0 = static_cast<uint64_t>(g - 1) << 4;
+			const uint32_t w0 = static_cast<uint32_t>((mis + (s0 << 4) + (sub << 2)) >> 2);   // word index, unwrapped
+			if (nstripes - s0 >= 16) {
+				uint32_t x[16];
+				if (sh == 0) {
+#pragma unroll
+					for (int j = 0; j < 16; j++) x[j] = ring32[(w0 + 4 * j) & WMASK];
+				} else {
+#pragma unroll
+					for (int j = 0; j < 16; j++)
+						x[j] = __funnelshift_r(ring32[(w0 + 4 * j) & WMASK], ring32[(w0 + 4 * j + 1) & WMASK], sh);
+				}
+#pragma unroll
+				for (int j = 0; j < 16; j++) acc = xxh_round(acc, x[j]);
+			} else {
+				const uint32_t cnt = static_cast<uint32_t>(nstripes - s0);
+				for (uint32_t j = 0; j < cnt; j++) {
+					uint32_t x = ring32[(w0 + 4 * j) & WMASK];
+					if (sh) x = __funnelshift_r(x, ring32[(w0 + 4 * j + 1) & WMASK], sh);
+					acc = xxh_round(acc, x);
+				}
+			}
+		}
+		__syncwarp();
+		if (g >= 1) issue(g - 1 + XXH_GROUPS);   // refill the slot batch g - 1 has just been read from
+	}
+	cp_async_wait<0>();
+	const uint32_t a0 = __shfl_sync(FULL_MASK, acc, 0, 4);
+	const uint32_t a1 = __shfl_sync(FULL_MASK, acc, 1, 4);
+	const uint32_t a2 = __shfl_sync(FULL_MASK, acc, 2, 4);
+	const uint32_t a3 = __shfl_sync(FULL_MASK, acc, 3, 4);
+	return xxh_finish<true>(a0, a1, a2, a3, n, p + (nstripes << 4), static_cast<uint32_t>(n & 15));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-cooperative copies (Write_Output, lib/lz4ada.adb:790-824 -- but exact: nothing is ever
 // written outside [dst, dst + n)).  Requires dst - src >= n or disjoint buffers.
 // ---------------------------------------------------------------------------------------------

@@ -114,7 +114,9 @@ xxh32_spans_kernel(const uint8_t *__restrict__ data, uint32_t n,
 		off = spans[idx].off;
 		len = spans[idx].len;
 	}
-	const uint32_t h = quad_xxh32<true, true>(data + off, len, lane);
+	extern __shared__ uint4 xxh_rings[];
+	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * XXH_RING_STRIDE);
+	const uint32_t h = quad_xxh32_stream(data + off, len, ring, lane);
 	if (valid && (lane & 3) == 0) out[idx] = h;
 }
 
@@ -144,7 +146,9 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 		}
 	}
 	if (!okay) len = 0;
-	const uint32_t h = quad_xxh32<true, true>(dst + base, len, lane);
+	extern __shared__ uint4 xxh_rings[];
+	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * XXH_RING_STRIDE);
+	const uint32_t h = quad_xxh32_stream(dst + base, len, ring, lane);
 	if (have && (lane & 3) == 0) {
 		digest[f] = h;
 		valid[f] = okay ? 1u : 0u;
@@ -515,8 +519,10 @@ int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_frames == 0) return LZ4B200_OK;
 	const uint32_t warps = (n_frames + 7) / 8;
-	xxh32_frames_kernel<<<(warps + 3) / 4, 128, 0, ctx->stream>>>(dst, n_frames, frames, desc, status, digest,
-								       valid);
+	const size_t smem = 4 * 8 * XXH_RING_STRIDE;
+	CK(cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	xxh32_frames_kernel<<<(warps + 3) / 4, 128, smem, ctx->stream>>>(dst, n_frames, frames, desc, status, digest,
+									  valid);
 	ctx->launches++;
 	CK(cudaGetLastError());
 	return LZ4B200_OK;
@@ -529,7 +535,9 @@ int lz4b200_xxh32_spans(lz4b200_ctx *ctx, const uint8_t *data, uint32_t n,
 	if (n == 0) return LZ4B200_OK;
 	const uint32_t warps = (n + 7) / 8;
 	const uint32_t grid = (warps + 3) / 4;
-	xxh32_spans_kernel<<<grid, 128, 0, ctx->stream>>>(data, n, spans, out);
+	const size_t smem = 4 * 8 * XXH_RING_STRIDE;
+	CK(cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	xxh32_spans_kernel<<<grid, 128, smem, ctx->stream>>>(data, n, spans, out);
 	ctx->launches++;
 	CK(cudaGetLastError());
 	return LZ4B200_OK;
