@@ -1,0 +1,104 @@
+--  LZ4Ada.Device -- thin binding of the device shim (include/lz4b200.h).
+--  UNCOMPILED in this image (no GNAT); see ada/README.md.
+--  Every function returns the shim's int: 0 ok, negative = CUDA / argument failure.  LZ4 data
+--  errors never travel in the return code; they come back in Block_Status records.
+with Interfaces;   use Interfaces;
+with Interfaces.C; use Interfaces.C;
+with System;
+
+private package LZ4Ada.Device is
+
+   type Context is new System.Address;   --  lz4b200_ctx *
+   type Stream  is new System.Address;   --  lz4b200_stream *
+
+   --  lz4b200_blk_desc
+   type Block_Desc is record
+      Src_Off    : Unsigned_64;   --  first payload byte (after the 4-byte size word)
+      Dst_Off    : Unsigned_64;   --  where the block's output starts
+      Src_Len    : Unsigned_32;   --  payload bytes, without the checksum trailer
+      Dst_Cap    : Unsigned_32;
+      Flags      : Unsigned_32;   --  Blk_Stored or Blk_Has_Checksum or ...
+      Hist_Avail : Unsigned_32;   --  frame position of the block start
+   end record with Convention => C;
+
+   Blk_Stored         : constant Unsigned_32 := 1;
+   Blk_Has_Checksum   : constant Unsigned_32 := 2;
+   Blk_Hash_Only      : constant Unsigned_32 := 4;
+   Blk_Chained        : constant Unsigned_32 := 8;
+   Blk_First_Of_Frame : constant Unsigned_32 := 16;
+
+   --  lz4b200_blk_status
+   type Block_Status is record
+      Code           : Unsigned_32;   --  0 ok, 1 block checksum, 2 ends after literals, 3 offset 0,
+                                      --  4 back-reference range, 5..9 Appendix C cases,
+                                      --  10 needs history (soft), 11 not run
+      Out_Len        : Unsigned_32;
+      Err_Pos        : Unsigned_32;
+      Aux            : Integer_32;
+      XXH32_Computed : Unsigned_32;
+      XXH32_Declared : Unsigned_32;
+   end record with Convention => C;
+
+   type Chain is record
+      First_Block, N_Blocks : Unsigned_32;
+      Dst_Off, Dst_Cap      : Unsigned_64;
+   end record with Convention => C;
+
+   type Frame_Blocks is record
+      First_Block, N_Blocks : Unsigned_32;
+   end record with Convention => C;
+
+   function Create (Device_Index : int; Cuda_Stream : System.Address; Ctx : out Context) return int
+     with Import, Convention => C, External_Name => "lz4b200_create";
+   function Destroy (Ctx : Context) return int
+     with Import, Convention => C, External_Name => "lz4b200_destroy";
+   function Last_Error (Ctx : Context) return Interfaces.C.Strings.chars_ptr
+     with Import, Convention => C, External_Name => "lz4b200_last_error";
+
+   function Alloc (Ctx : Context; Bytes : size_t; Ptr : out System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_alloc";
+   function Free (Ctx : Context; Ptr : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_free";
+   function Alloc_Host (Ctx : Context; Bytes : size_t; Ptr : out System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_alloc_host";
+   function Free_Host (Ctx : Context; Ptr : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_free_host";
+   function H2D (Ctx : Context; Dst_Dev, Src_Host : System.Address; Bytes : size_t) return int
+     with Import, Convention => C, External_Name => "lz4b200_h2d";
+   function D2H (Ctx : Context; Dst_Host, Src_Dev : System.Address; Bytes : size_t) return int
+     with Import, Convention => C, External_Name => "lz4b200_d2h";
+   function Sync (Ctx : Context) return int
+     with Import, Convention => C, External_Name => "lz4b200_sync";
+
+   --  K1 (+K2): independent blocks, fused block XXH32   (lib/lz4ada.adb:661-904)
+   function Decode_Blocks (Ctx : Context; Src, Dst : System.Address; N_Blocks : Unsigned_32;
+                           Desc, Status : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_decode_blocks";
+   --  K4: chains (linked frames, exact-placement retries)
+   function Decode_Linked (Ctx : Context; Src, Dst : System.Address; N_Chains : Unsigned_32;
+                           Chains, Desc, Status : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_decode_linked";
+   --  K3: content checksum per frame                      (lib/lz4ada.adb:709-714, 942-1017)
+   function XXH32_Frames (Ctx : Context; Dst : System.Address; N_Frames : Unsigned_32;
+                          Frames, Desc, Status, Digest, Valid : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_xxh32_frames";
+   --  K5: size pre-pass
+   function Size_Blocks (Ctx : Context; Src : System.Address; N_Blocks : Unsigned_32;
+                         Desc, Status : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_size_blocks";
+
+   --  single-block path under Decompressor.Update
+   function Stream_Create (Ctx : Context; Max_Block : Unsigned_32; S : out Stream) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_create";
+   function Stream_Destroy (S : Stream) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_destroy";
+   function Stream_Reset (S : Stream) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_reset";
+   function Stream_Block (S : Stream; Host_Src : System.Address; Src_Len, Flags : Unsigned_32;
+                          Hash_Content : int; Host_Dst : System.Address; Dst_Cap : Unsigned_32;
+                          Status : out Block_Status) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_block";
+   function Stream_Digest (S : Stream; XXH32 : out Unsigned_32) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_digest";
+
+end LZ4Ada.Device;

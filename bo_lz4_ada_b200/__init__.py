@@ -136,6 +136,9 @@ _SIGNATURES = {
     "lz4b200_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "lz4b200_set_tuning": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "lz4b200_get_tuning": (ctypes.c_int, [ctypes.c_void_p]),
+    "lz4b200_use_lane": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "lz4b200_sync_all": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "lz4b200_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_alloc_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -200,6 +203,8 @@ _SIGNATURES = {
     "lz4ada_batch_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "lz4ada_batch_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "lz4ada_batch_run_pipelined": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_uint32]),
     "lz4ada_batch_results": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BatchResult)]),
     "lz4ada_batch_message": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
     "lz4ada_batch_free": (None, [ctypes.c_void_p]),

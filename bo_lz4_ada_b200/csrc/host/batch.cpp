@@ -641,6 +641,88 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 	return LZ4ADA_OK;
 }
 
+// Pipelined device stage for host buffers.  Chunks are runs of consecutive streams; the tables are
+// already on the device (lz4ada_batch_upload with src_host == NULL), so each chunk is
+// H2D(compressed) -> K1 -> K4 -> K3 -> D2H(status, digests) -> D2H(output) on its own lane.
+int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t *dst_host, uint8_t *src_dev,
+			       uint8_t *dst_dev, uint32_t n_chunks)
+{
+	if (!b || !b->ctx || !src_host || !dst_host) return LZ4ADA_ASSERTION_ERROR;
+	lz4b200_ctx *ctx = b->ctx;
+	const size_t nb = b->descs.size(), nh = b->hash_frames.size(), nc = b->chains.size(), ni = b->items.size();
+	if (!nb || !b->tables_uploaded || !b->placed) return LZ4ADA_ASSERTION_ERROR;
+	if (n_chunks < 1) n_chunks = 1;
+	if (n_chunks > ni) n_chunks = uint32_t(ni);
+	// one K1 shape for all chunks: pick it from the whole batch, not from a chunk's block count
+	const int saved_tuning = lz4b200_get_tuning(ctx);
+	if (saved_tuning == 0) {
+		const uint64_t per = uint64_t(lz4b200_sm_count(ctx) > 0 ? lz4b200_sm_count(ctx) : 148) * 16u;
+		lz4b200_set_tuning(ctx, nb >= 8 * per ? 8 : nb >= 4 * per ? 4 : nb >= 2 * per ? 2 : 1);
+	}
+	int rc = LZ4ADA_OK;
+	size_t chain_pos = 0, hash_pos = 0;
+	for (uint32_t c = 0; c < n_chunks && rc == LZ4ADA_OK; c++) {
+		const size_t i0 = ni * c / n_chunks, i1 = ni * (c + 1) / n_chunks;
+		if (i0 == i1) continue;
+		const ItemPlan &first = b->items[i0], &last = b->items[i1 - 1];
+		const uint32_t b0 = first.first_block, b1 = last.first_block + last.n_blocks;
+		// source bytes of the chunk: streams are taken in the order given, usually back to back
+		uint64_t s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
+		for (size_t i = i0; i < i1; i++) {
+			const ItemPlan &it = b->items[i];
+			s_lo = std::min(s_lo, it.src_off);
+			s_hi = std::max(s_hi, it.src_off + it.src_len);
+			if (it.n_blocks) {
+				d_lo = std::min(d_lo, it.dst_off);
+				d_hi = std::max(d_hi, it.dst_off + it.dst_cap);
+			}
+		}
+		size_t c0 = chain_pos, h0 = hash_pos;
+		while (chain_pos < nc && b->chains[chain_pos].first_block < b1) chain_pos++;
+		while (hash_pos < nh && b->hash_frames[hash_pos].first_block < b1) hash_pos++;
+		const size_t ncc = chain_pos - c0, nhc = hash_pos - h0;
+		bool bad = lz4b200_use_lane(ctx, int(c % 3) + 1) != LZ4B200_OK;
+		bad = bad || lz4b200_h2d(ctx, src_dev + s_lo, src_host + s_lo, s_hi - s_lo) != LZ4B200_OK;
+		if (b1 > b0)
+			bad = bad || lz4b200_decode_blocks(ctx, src_dev, dst_dev, b1 - b0, b->d_desc + b0, b->d_status + b0) != LZ4B200_OK;
+		// chains and frame tables index blocks globally, so they get the un-offset arrays
+		if (ncc)
+			bad = bad || lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(ncc), b->d_chains + c0, b->d_desc, b->d_status) != LZ4B200_OK;
+		if (nhc)
+			bad = bad || lz4b200_xxh32_frames(ctx, dst_dev, uint32_t(nhc), b->d_hash_frames + h0, b->d_desc, b->d_status,
+							   b->d_digest + h0, b->d_digest + nh + h0) != LZ4B200_OK;
+		if (b1 > b0)
+			bad = bad || lz4b200_d2h(ctx, b->h_status + b0, b->d_status + b0, sizeof(lz4b200_blk_status) * (b1 - b0)) != LZ4B200_OK;
+		if (nhc) {
+			bad = bad || lz4b200_d2h(ctx, b->h_digest + h0, b->d_digest + h0, 4 * nhc) != LZ4B200_OK;
+			bad = bad || lz4b200_d2h(ctx, b->h_digest + nh + h0, b->d_digest + nh + h0, 4 * nhc) != LZ4B200_OK;
+		}
+		if (d_hi > d_lo) bad = bad || lz4b200_d2h(ctx, dst_host + d_lo, dst_dev + d_lo, d_hi - d_lo) != LZ4B200_OK;
+		if (bad) rc = LZ4ADA_DEVICE_ERROR;
+	}
+	if (lz4b200_sync_all(ctx) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+	lz4b200_use_lane(ctx, 0);
+	lz4b200_set_tuning(ctx, saved_tuning);
+	if (rc != LZ4ADA_OK) return rc;
+	bool any_slow = false;
+	for (ItemPlan &it : b->items) {
+		it.slow = fold_item(b, it, false, [&](const FramePlan &fp, uint32_t &value) {
+			if (fp.hash_slot == 0xffffffffu || !b->h_digest[nh + fp.hash_slot]) return false;
+			value = b->h_digest[fp.hash_slot];
+			return true;
+		});
+		if (it.slow) any_slow = true;
+	}
+	if (any_slow) {
+		if (run_slow_items(b, src_dev, dst_dev)) return LZ4ADA_DEVICE_ERROR;
+		for (const ItemPlan &it : b->items)
+			if (it.slow && it.out_len && lz4b200_d2h(ctx, dst_host + it.dst_off, dst_dev + it.dst_off, it.out_len) != LZ4B200_OK)
+				return LZ4ADA_DEVICE_ERROR;
+		if (lz4b200_sync(ctx) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+	}
+	return LZ4ADA_OK;
+}
+
 int lz4ada_batch_results(const lz4ada_batch *b, lz4ada_batch_result *results)
 {
 	if (!b || !results) return LZ4ADA_ASSERTION_ERROR;
@@ -664,6 +746,53 @@ const char *lz4ada_batch_message(const lz4ada_batch *b, uint32_t item)
 
 void lz4ada_batch_free(lz4ada_batch *b) { delete b; }
 
+// Device scratch of lz4ada_batch_decompress, kept between calls (cudaMalloc of several GB per call
+// would dominate); one pool per context, freed with the process.
+struct ScratchPool {
+	lz4b200_ctx *ctx = nullptr;
+	uint8_t *d_src = nullptr, *d_dst = nullptr;
+	uint64_t cap_src = 0, cap_dst = 0;
+	// table buffers handed to (and taken back from) the batch of the current call
+	lz4b200_blk_desc *d_desc = nullptr;
+	lz4b200_blk_status *d_status = nullptr, *h_status = nullptr;
+	size_t cap_blocks = 0;
+	lz4b200_frame_blocks *d_hash_frames = nullptr;
+	uint32_t *d_digest = nullptr, *h_digest = nullptr;
+	size_t cap_hash = 0;
+};
+static ScratchPool g_pool[8];
+
+static ScratchPool *pool_for(lz4b200_ctx *ctx)
+{
+	for (ScratchPool &p : g_pool)
+		if (p.ctx == ctx) return &p;
+	for (ScratchPool &p : g_pool)
+		if (!p.ctx) {
+			p.ctx = ctx;
+			return &p;
+		}
+	return nullptr;
+}
+
+static bool pool_reserve(ScratchPool *p, uint64_t src_bytes, uint64_t dst_bytes)
+{
+	if (src_bytes > p->cap_src) {
+		if (p->d_src) lz4b200_free(p->ctx, p->d_src);
+		p->d_src = nullptr;
+		p->cap_src = 0;
+		if (lz4b200_alloc(p->ctx, src_bytes + 64, reinterpret_cast<void **>(&p->d_src)) != LZ4B200_OK) return false;
+		p->cap_src = src_bytes;
+	}
+	if (dst_bytes > p->cap_dst) {
+		if (p->d_dst) lz4b200_free(p->ctx, p->d_dst);
+		p->d_dst = nullptr;
+		p->cap_dst = 0;
+		if (lz4b200_alloc(p->ctx, dst_bytes + 64, reinterpret_cast<void **>(&p->d_dst)) != LZ4B200_OK) return false;
+		p->cap_dst = dst_bytes;
+	}
+	return true;
+}
+
 int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes, uint8_t *dst_host,
 			    uint64_t dst_bytes, uint32_t n_items, lz4ada_batch_item *items, int reservation,
 			    lz4ada_batch_result *results, char *messages, size_t message_stride)
@@ -678,18 +807,50 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 		if (!b->ctx) return LZ4ADA_DEVICE_ERROR;
 	}
 	ctx = b->ctx;
-	uint8_t *d_src = nullptr, *d_dst = nullptr;
-	if (lz4b200_alloc(ctx, src_bytes + 64, reinterpret_cast<void **>(&d_src)) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
-	rc = lz4ada_batch_upload(b, src_host, d_src);
+	ScratchPool *pool = pool_for(ctx);
+	if (!pool) return LZ4ADA_DEVICE_ERROR;
 	const uint64_t need = lz4ada_batch_output_bytes(b);
-	if (rc == LZ4ADA_OK && need > dst_bytes) rc = LZ4ADA_ASSERTION_ERROR;
-	if (rc == LZ4ADA_OK && lz4b200_alloc(ctx, need + 64, reinterpret_cast<void **>(&d_dst)) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
-	if (rc == LZ4ADA_OK) rc = lz4ada_batch_run(b, d_src, d_dst);
-	if (rc == LZ4ADA_OK) {
-		// bring back exactly what each stream produced
-		for (const ItemPlan &it : b->items)
-			if (it.out_len && lz4b200_d2h(ctx, dst_host + it.dst_off, d_dst + it.dst_off, it.out_len) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
-		if (lz4b200_sync(ctx) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+	if (need > dst_bytes) return LZ4ADA_ASSERTION_ERROR;
+	if (!pool_reserve(pool, src_bytes, need)) return LZ4ADA_DEVICE_ERROR;
+	uint8_t *d_src = pool->d_src, *d_dst = pool->d_dst;
+	// lend pooled table buffers to the batch when they are large enough (cudaMalloc / cudaMallocHost
+	// per call cost ~100 ms, several times the device stage)
+	const size_t nbk = b->descs.size(), nhk = b->hash_frames.size();
+	const bool lend_blocks = nbk && pool->cap_blocks >= nbk, lend_hash = nhk && pool->cap_hash >= nhk;
+	if (lend_blocks) { b->d_desc = pool->d_desc; b->d_status = pool->d_status; b->h_status = pool->h_status; }
+	if (lend_hash) { b->d_hash_frames = pool->d_hash_frames; b->d_digest = pool->d_digest; b->h_digest = pool->h_digest; }
+	struct Return {
+		lz4ada_batch *b; ScratchPool *p; size_t nbk, nhk;
+		~Return()
+		{
+			// keep the (possibly freshly allocated) buffers for the next call instead of freeing them
+			if (b->d_desc && nbk >= p->cap_blocks) {
+				if (p->d_desc && p->d_desc != b->d_desc) { lz4b200_free(p->ctx, p->d_desc); lz4b200_free(p->ctx, p->d_status); lz4b200_free_host(p->ctx, p->h_status); }
+				p->d_desc = b->d_desc; p->d_status = b->d_status; p->h_status = b->h_status; p->cap_blocks = nbk;
+			}
+			if (b->d_desc == p->d_desc) { b->d_desc = nullptr; b->d_status = nullptr; b->h_status = nullptr; }
+			if (b->d_hash_frames && nhk >= p->cap_hash) {
+				if (p->d_hash_frames && p->d_hash_frames != b->d_hash_frames) { lz4b200_free(p->ctx, p->d_hash_frames); lz4b200_free(p->ctx, p->d_digest); lz4b200_free_host(p->ctx, p->h_digest); }
+				p->d_hash_frames = b->d_hash_frames; p->d_digest = b->d_digest; p->h_digest = b->h_digest; p->cap_hash = nhk;
+			}
+			if (b->d_hash_frames == p->d_hash_frames) { b->d_hash_frames = nullptr; b->d_digest = nullptr; b->h_digest = nullptr; }
+		}
+	} give_back{b, pool, nbk, nhk};
+	const uint64_t plain_guess = need;
+	if (b->placed && b->descs.size()) {
+		// fast shape: placement is known without touching the device -> pipeline H2D / kernels / D2H
+		rc = lz4ada_batch_upload(b, nullptr, nullptr);   // tables only
+		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 29)));   // ~512 MiB of output each
+		if (rc == LZ4ADA_OK) rc = lz4ada_batch_run_pipelined(b, src_host, dst_host, d_src, d_dst, chunks);
+	} else {
+		rc = lz4ada_batch_upload(b, src_host, d_src);
+		if (rc == LZ4ADA_OK) rc = lz4ada_batch_run(b, d_src, d_dst);
+		if (rc == LZ4ADA_OK) {
+			// bring back exactly what each stream produced
+			for (const ItemPlan &it : b->items)
+				if (it.out_len && lz4b200_d2h(ctx, dst_host + it.dst_off, d_dst + it.dst_off, it.out_len) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+			if (lz4b200_sync(ctx) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
+		}
 	}
 	if (rc == LZ4ADA_OK && results) lz4ada_batch_results(b, results);
 	if (rc == LZ4ADA_OK && messages && message_stride)
@@ -704,8 +865,6 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 			items[k].dst_off = b->items[k].dst_off;
 			items[k].dst_cap = b->items[k].dst_cap;
 		}
-	if (d_src) lz4b200_free(ctx, d_src);
-	if (d_dst) lz4b200_free(ctx, d_dst);
 	return rc;
 }
 

@@ -284,7 +284,8 @@ size_blocks_kernel(const uint8_t *__restrict__ src, uint32_t n_blocks,
 struct lz4b200_ctx {
 	int device = 0;
 	int sm_count = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;      // the lane in use (lz4b200_use_lane)
+	cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // lane 0 = primary stream
 	bool own_stream = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint64_t launches = 0;
@@ -331,6 +332,13 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 		}
 		ctx->own_stream = true;
 	}
+	ctx->lanes[0] = ctx->stream;
+	{
+		// once per context, not per launch: the K3 kernels need > 48 KiB of dynamic shared memory
+		const int smem = 4 * 8 * XXH_RING_STRIDE;
+		cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	}
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
 	*out = ctx;
@@ -341,10 +349,15 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 {
 	if (!ctx) return LZ4B200_OK;
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
+	cudaStreamSynchronize(ctx->lanes[0]);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	for (int i = 1; i < 4; i++)
+		if (ctx->lanes[i]) {
+			cudaStreamSynchronize(ctx->lanes[i]);
+			cudaStreamDestroy(ctx->lanes[i]);
+		}
+	if (ctx->own_stream) cudaStreamDestroy(ctx->lanes[0]);
 	delete ctx;
 	return LZ4B200_OK;
 }
@@ -352,6 +365,25 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 const char *lz4b200_last_error(const lz4b200_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 int lz4b200_sm_count(const lz4b200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lz4b200_use_lane(lz4b200_ctx *ctx, int lane)
+{
+	if (!ctx || lane < 0 || lane >= 4) return LZ4B200_ERR_ARG;
+	if (!ctx->lanes[lane]) {
+		CK(cudaSetDevice(ctx->device));
+		CK(cudaStreamCreateWithFlags(&ctx->lanes[lane], cudaStreamNonBlocking));
+	}
+	ctx->stream = ctx->lanes[lane];
+	return LZ4B200_OK;
+}
+
+int lz4b200_sync_all(lz4b200_ctx *ctx)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	for (int i = 0; i < 4; i++)
+		if (ctx->lanes[i]) CK(cudaStreamSynchronize(ctx->lanes[i]));
+	return LZ4B200_OK;
+}
 
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
@@ -361,6 +393,8 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
 }
+
+int lz4b200_get_tuning(const lz4b200_ctx *ctx) { return ctx ? ctx->blocks_per_warp : 0; }
 
 int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr)
 {
@@ -520,7 +554,6 @@ int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames
 	if (n_frames == 0) return LZ4B200_OK;
 	const uint32_t warps = (n_frames + 7) / 8;
 	const size_t smem = 4 * 8 * XXH_RING_STRIDE;
-	CK(cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 	xxh32_frames_kernel<<<(warps + 3) / 4, 128, smem, ctx->stream>>>(dst, n_frames, frames, desc, status, digest,
 									  valid);
 	ctx->launches++;
@@ -536,7 +569,6 @@ int lz4b200_xxh32_spans(lz4b200_ctx *ctx, const uint8_t *data, uint32_t n,
 	const uint32_t warps = (n + 7) / 8;
 	const uint32_t grid = (warps + 3) / 4;
 	const size_t smem = 4 * 8 * XXH_RING_STRIDE;
-	CK(cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 	xxh32_spans_kernel<<<grid, 128, smem, ctx->stream>>>(data, n, spans, out);
 	ctx->launches++;
 	CK(cudaGetLastError());

@@ -136,6 +136,15 @@ uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx);
  * -1 = the one-warp-per-block kernel that is also the exact fallback. */
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp);
 
+int lz4b200_get_tuning(const lz4b200_ctx *ctx);
+
+/* A context owns up to four CUDA streams ("lanes"; lane 0 is the primary one given to / made by
+ * lz4b200_create).  Every call enqueues on the lane selected last.  The batch scheduler uses them
+ * to overlap H2D of one chunk, kernels of another and D2H of a third; no kernel waits on another
+ * lane.  lz4b200_sync_all waits for all lanes. */
+int lz4b200_use_lane(lz4b200_ctx *ctx, int lane);
+int lz4b200_sync_all(lz4b200_ctx *ctx);
+
 /* Device and pinned-host memory, so that the Ada side never links libcudart. */
 int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr);
 int lz4b200_free(lz4b200_ctx *ctx, void *dev_ptr);
@@ -348,6 +357,12 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev);
 int lz4ada_batch_results(const lz4ada_batch *b, lz4ada_batch_result *results);
 const char *lz4ada_batch_message(const lz4ada_batch *b, uint32_t item);
 void lz4ada_batch_free(lz4ada_batch *b);
+
+/* Host buffers in and out with the device stage cut into `n_chunks` groups of streams that are
+ * pipelined over the context's lanes: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of
+ * chunk k.  src_dev / dst_dev are device scratch buffers sized like lz4ada_batch_upload / _run. */
+int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t *dst_host,
+		uint8_t *src_dev, uint8_t *dst_dev, uint32_t n_chunks);
 
 /* One call, host buffers in and out: plan + H2D + kernels + D2H.  This is the
  * end-to-end call bench.py times for `e2e`.  items[k].dst_off / dst_cap are updated with

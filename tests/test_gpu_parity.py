@@ -510,3 +510,55 @@ def test_property_roundtrip_large(ctx):
     b.close()
     ctx.free(d_src)
     ctx.free(d_dst)
+
+
+def test_pipelined_host_path(ctx, oracle):
+    """lz4ada_batch_run_pipelined (the device stage of the e2e call, chunks on separate CUDA streams)
+    and the one-shot lz4ada_batch_decompress: good, slow-path and corrupted streams mixed."""
+    import ctypes
+    c = corpus.build_corpus(24 << 20, 1 << 20, 4, kinds=("text", "rle", "random"), keep_plain=True)
+    text = corpus.text_like(200000, seed=77)
+    extra = [corpus.build_frame(text, 4, False, True, block_size=30000),              # short interior blocks
+             corpus.build_frame(text, 4, True, True, independent=False),              # linked
+             _read("corruptedcntchcksm.err"), _read("backrefoverflow.err"), _read("t300k.lz4")]
+    streams = [bytes(c["src"][o:o + n]) for o, n in c["items"]] + extra
+    plains = list(c["plain"]) + [text, text, None, None, _read("t300k.bin")]
+    src = b"".join(streams)
+    offs, pos = [], 0
+    for st in streams:
+        offs.append((pos, len(st)))
+        pos += len(st)
+    # (a) explicit pipelined run, 5 chunks
+    b = lz.Batch(ctx, src, offs)
+    need = b.output_bytes
+    d_src, d_dst = ctx.alloc(len(src)), ctx.alloc(need)
+    host_out = bytearray(need + 64)
+    addr_out = (ctypes.c_uint8 * len(host_out)).from_buffer(host_out)
+    assert lz.lib().lz4ada_batch_upload(b._h, None, None) == 0
+    rc = lz.lib().lz4ada_batch_run_pipelined(b._h, b.src_addr, addr_out, d_src, d_dst, 5)
+    assert rc == 0
+    for st, plain, r in zip(streams, plains, b.results()):
+        oexc, oout, oeof, omsg = oracle.decode_stream(st, chunk=0, out_cap=(len(plain) if plain else 1 << 16) + 64)
+        assert (r["exception"], r["message"]) == (oexc, omsg)
+        assert bytes(host_out[r["dst_off"]:r["dst_off"] + r["out_len"]]) == oout
+        if plain is not None:
+            assert oout == plain
+    b.close()
+    ctx.free(d_src)
+    ctx.free(d_dst)
+    # (b) the one-shot public call
+    items = (lz.BatchItem * len(offs))()
+    for k, (o, n) in enumerate(offs):
+        items[k].src_off, items[k].src_len = o, n
+    results = (lz.BatchResult * len(offs))()
+    msgs = ctypes.create_string_buffer(256 * len(offs))
+    out2 = bytearray(need + 64)
+    addr2 = (ctypes.c_uint8 * len(out2)).from_buffer(out2)
+    rc = lz.lib().lz4ada_batch_decompress(ctx.handle, src, len(src), addr2, need, len(offs), items,
+                                          lz.RESERVATIONS["For_All"], results, msgs, 256)
+    assert rc == 0
+    for k, (st, plain) in enumerate(zip(streams, plains)):
+        oexc, oout, oeof, omsg = oracle.decode_stream(st, chunk=0, out_cap=(len(plain) if plain else 1 << 16) + 64)
+        assert lz.EXC_NAMES[results[k].exception] == oexc
+        assert msgs.raw[256 * k:256 * (k + 1)].split(b"\0")[0].decode() == omsg
+        assert bytes(out2[results[k].dst_off:results[k].dst_off + results[k].out_len]) == oout
