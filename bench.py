@@ -322,7 +322,7 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
         "kernel_ms": {"k1_decode_blocks": k1, "k3_xxh32_frames": float(np.mean(k3_ms)) if k3_ms else 0.0},
-        "roofline": {"bound": "hbm", "kernel": "decode_blocks_kernel (K1)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "decode_blocks_v2_kernel (K1)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(k1_bytes),
                      "whole_step_frac": (k1_bytes + traffic["checksum_reread"]) / (ms_per_step / 1e3) / 1e9 / peak},
