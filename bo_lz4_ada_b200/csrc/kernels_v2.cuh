@@ -273,13 +273,62 @@ __device__ __forceinline__ bool copy_batch(const uint8_t *__restrict__ sg, uint8
 	return true;
 }
 
+// One block of a chain by one warp through the batch machinery (lane 0 walks the token chain).
+// Positions are relative to `frame_out` (the start of the frame's flat output), so a match may
+// reach back across block boundaries; pos advances by what the block produced.  Returns false when
+// the block needs the exact routine.
+__device__ __forceinline__ bool chain_block_fast(const uint8_t *__restrict__ s, uint32_t n, uint8_t *frame_out,
+						 uint32_t &pos, uint32_t cap_abs, SeqDesc *sd, uint8_t *tile,
+						 int lane)
+{
+	uint32_t ip = 0;
+	while (ip < n) {
+		uint32_t cnt = 0;
+		bool fb = false;
+		if (lane == 0) {
+			while (cnt < 32 && ip < n) {
+				const uint32_t t = ld_u8<true>(s + ip);
+				uint32_t lit = t >> 4, ml = t & 15, p = ip + 1, nxt;
+				if (lit == 15 || ml == 15) {
+					if (!parse_extended(s, n, p, lit, ml, nxt)) { fb = true; break; }
+				} else {
+					const uint32_t q = p + lit;
+					if (q + 2 <= n) {
+						ml += 4;
+						nxt = q + 2;
+					} else if (q == n && ml == 0) {
+						nxt = n;
+					} else {
+						fb = true;
+						break;
+					}
+				}
+				*reinterpret_cast<uint2 *>(sd + cnt) = make_uint2(p, lit | (ml << 16));
+				cnt++;
+				ip = nxt;
+			}
+		}
+		__syncwarp();
+		fb = __shfl_sync(FULL_MASK, fb ? 1 : 0, 0) != 0;
+		cnt = __shfl_sync(FULL_MASK, cnt, 0);
+		ip = __shfl_sync(FULL_MASK, ip, 0);
+		if (fb) return false;
+		if (cnt == 0) break;
+		uint32_t total = 0;
+		if (!copy_batch(s, frame_out, pos, cap_abs, sd, cnt, lane, tile, total)) return false;
+		pos += total;
+		__syncwarp();
+	}
+	return true;
+}
+
 // One warp, G blocks (first_block .. first_block + G - 1).  sd = this warp's [G][32] descriptors.
 template <int G>
 __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
 					     uint32_t first_block, const lz4b200_blk_desc *__restrict__ desc,
 					     lz4b200_blk_status *status, SeqDesc *sd, uint8_t *tile, int lane)
 {
-	static_assert(G >= 1 && G <= 8, "one quad per block for the fused checksum");
+	static_assert(G >= 1 && G <= 32, "one lane per block");
 	uint32_t state = LS_IDLE;
 	const uint8_t *s = src;
 	uint8_t *o = dst;
@@ -297,19 +346,24 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 		}
 	}
 
-	// ---- fused block checksum: quad q hashes block q, G chains per warp (lib/lz4ada.adb:698-707) ----
-	{
+	// ---- fused block checksum: quad q hashes block 8 * pass + q, eight chains per warp at a time
+	//      (lib/lz4ada.adb:698-707) ----
+#pragma unroll 1
+	for (int pass = 0; pass * 8 < G; pass++) {
 		const int q = lane >> 2;
-		const int qq = q < G ? q : 0;
+		const int blk = pass * 8 + q;
+		const int qq = blk < G ? blk : 0;
 		const uint8_t *sq = shfl_cptr(s, qq);
 		const uint32_t nq = __shfl_sync(FULL_MASK, n, qq);
 		const uint32_t fq = __shfl_sync(FULL_MASK, flags, qq);
 		const uint32_t stq = __shfl_sync(FULL_MASK, state, qq);
-		const bool want = q < G && stq == LS_RUN && (fq & LZ4B200_BLK_HAS_CHECKSUM);
+		const bool want = blk < G && stq == LS_RUN && (fq & LZ4B200_BLK_HAS_CHECKSUM);
 		if (__any_sync(FULL_MASK, want)) {
 			const uint32_t h = quad_xxh32_prologue(sq, want ? nq : 0, lane);
-			const uint32_t hq = __shfl_sync(FULL_MASK, h, (lane * 4) & 31);
-			if (state == LS_RUN && (flags & LZ4B200_BLK_HAS_CHECKSUM)) {
+			// lane g (block g) of this pass picks up the digest of its quad
+			const int src_lane = ((lane - pass * 8) * 4) & 31;
+			const uint32_t hq = __shfl_sync(FULL_MASK, h, src_lane);
+			if (lane >= pass * 8 && lane < pass * 8 + 8 && state == LS_RUN && (flags & LZ4B200_BLK_HAS_CHECKSUM)) {
 				const uint8_t *t = s + n;
 				declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) |
 					   (ld_u8<true>(t + 3) << 24);

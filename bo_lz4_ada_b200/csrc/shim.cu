@@ -57,6 +57,8 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 	const int lane = threadIdx.x & 31;
 	const uint32_t c = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
 	if (c >= n_chains) return;
+	__shared__ SeqDesc sd[K1_WARPS][SD_STRIDE];
+	__shared__ uint4 tiles[K1_WARPS][(TILE_BYTES + 32) / 16];
 	const lz4b200_chain ch = chains[c];
 	uint8_t *out = dst + ch.dst_off;
 	uint64_t pos = 0;         // chain-relative output position
@@ -81,7 +83,37 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 		const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
 		const uint64_t room = ch.dst_cap - pos;
 		const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
-		process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
+		// fast path (kernels_v2.cuh) when the frame position fits 32 bits and the block is an
+		// ordinary compressed one; the exact routine otherwise and for anything unusual
+		bool fast_done = false;
+		if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_HASH_ONLY)) && fpos + cap < 0xfff00000ull) {
+			uint32_t computed = 0, declared = 0;
+			bool sum_ok = true;
+			const uint8_t *s = src + d.src_off;
+			if (d.flags & LZ4B200_BLK_HAS_CHECKSUM) {
+				const uint8_t *t = s + d.src_len;
+				declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) |
+					   (ld_u8<true>(t + 3) << 24);
+				computed = quad_xxh32_prologue(s, d.src_len, lane);
+				sum_ok = computed == declared;
+			}
+			if (sum_ok) {
+				uint32_t p32 = static_cast<uint32_t>(fpos);
+				if (chain_block_fast(s, d.src_len, out + frame_start, p32, static_cast<uint32_t>(fpos) + cap,
+						     sd[threadIdx.x >> 5], reinterpret_cast<uint8_t *>(tiles[threadIdx.x >> 5]), lane)) {
+					fast_done = true;
+					if (lane == 0) {
+						status[b].code = LZ4B200_ST_OK;
+						status[b].out_len = p32 - static_cast<uint32_t>(fpos);
+						status[b].err_pos = 0;
+						status[b].aux = 0;
+						status[b].xxh32_computed = computed;
+						status[b].xxh32_declared = declared;
+					}
+				}
+			}
+		}
+		if (!fast_done) process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
 		__syncwarp();
 		const uint32_t code = status[b].code;      // lane 0 wrote it; visible after __syncwarp
 		const uint32_t out_len = status[b].out_len;
@@ -388,7 +420,7 @@ int lz4b200_sync_all(lz4b200_ctx *ctx)
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
 	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
-		     blocks_per_warp != 4 && blocks_per_warp != 8))
+		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16))
 		return LZ4B200_ERR_ARG;
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
@@ -513,7 +545,7 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 	if (g == 0) {
 		// keep at least ~16 warps per SM busy; more blocks per warp = cheaper token-chain walking
 		const uint32_t per = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u;
-		g = n_blocks >= 8 * per ? 8 : n_blocks >= 4 * per ? 4 : n_blocks >= 2 * per ? 2 : 1;
+		g = n_blocks >= 16 * per + per ? 16 : n_blocks >= 8 * per ? 8 : n_blocks >= 4 * per ? 4 : n_blocks >= 2 * per ? 2 : 1;
 	}
 	if (g < 0) {
 		const uint32_t grid = (n_blocks + K1_WARPS - 1) / K1_WARPS;
@@ -522,6 +554,7 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		const uint32_t warps = (n_blocks + g - 1) / g;
 		const uint32_t grid = (warps + K1_WARPS - 1) / K1_WARPS;
 		switch (g) {
+		case 16: decode_blocks_v2_kernel<16><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
 		case 8: decode_blocks_v2_kernel<8><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
 		case 4: decode_blocks_v2_kernel<4><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;
 		case 2: decode_blocks_v2_kernel<2><<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_blocks, desc, status); break;

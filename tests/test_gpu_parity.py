@@ -194,7 +194,7 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
         assert out == oout, stem
 
 
-@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8])
+@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16])
 def test_batch_k1_variants(ctx, oracle, g):
     """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8 blocks per warp): good vectors,
     synthetic frames and corrupted streams must all come out exactly as the oracle says."""
@@ -436,7 +436,7 @@ def _py_decode(block):
     return bytes(out)
 
 
-@pytest.mark.parametrize("g", [-1, 1, 8])
+@pytest.mark.parametrize("g", [-1, 1, 8, 16])
 def test_k1_overlap_matrix_direct(ctx, oracle, g):
     """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
     warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
