@@ -483,10 +483,12 @@ static int decrease_data_size_remaining(lzo_ctx *c, uint64_t n)
  * bytes; this copy moves 8-byte slices too but never writes outside [dst, dst + n): the last
  * slice is placed so that it ends exactly at the end.  Ranges that overlap closer than eight
  * bytes (history replay with src just ahead of dst) fall back to memmove. */
-static void copy_exact(uint8_t *dst, const uint8_t *src, int n)
+static inline void copy_exact(uint8_t *dst, const uint8_t *src, int n)
 {
 	ptrdiff_t gap = src > dst ? src - dst : dst - src;
-	if (n >= 8 && gap >= 8 && n <= 64) {
+	if (gap < 8 || n > 64) {
+		memmove(dst, src, (size_t)n);
+	} else if (n >= 8) {
 		int i;
 		uint64_t last, v;
 		memcpy(&last, src + n - 8, 8);
@@ -495,12 +497,20 @@ static void copy_exact(uint8_t *dst, const uint8_t *src, int n)
 			memcpy(dst + i, &v, 8);
 		}
 		memcpy(dst + n - 8, &last, 8);
-	} else if (n < 8 && gap >= 8) {
-		int i;
-		for (i = 0; i < n; i++)
-			dst[i] = src[i];
-	} else {
-		memmove(dst, src, (size_t)n);
+	} else if (n >= 4) {           /* two overlapping 4-byte moves */
+		uint32_t a, b;
+		memcpy(&a, src, 4);
+		memcpy(&b, src + n - 4, 4);
+		memcpy(dst, &a, 4);
+		memcpy(dst + n - 4, &b, 4);
+	} else if (n >= 2) {
+		uint16_t a, b;
+		memcpy(&a, src, 2);
+		memcpy(&b, src + n - 2, 2);
+		memcpy(dst, &a, 2);
+		memcpy(dst + n - 2, &b, 2);
+	} else if (n == 1) {
+		dst[0] = src[0];
 	}
 }
 

@@ -562,3 +562,22 @@ def test_pipelined_host_path(ctx, oracle):
         assert lz.EXC_NAMES[results[k].exception] == oexc
         assert msgs.raw[256 * k:256 * (k + 1)].split(b"\0")[0].decode() == omsg
         assert bytes(out2[results[k].dst_off:results[k].dst_off + results[k].out_len]) == oout
+
+
+def test_cli_unlz4ada_b200(ctx):
+    """The stdin -> stdout tool (counterpart of tool_unlz4ada_simple; test_run.sh's check: rv = 0 and
+    sha256(out) == sha256(.bin)) on every good vector, and a non-zero exit with the library's
+    exception text on an error vector."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "unlz4ada_b200")
+    if not os.path.exists(exe):
+        pytest.skip("tools/unlz4ada_b200 not built")
+    for stem in GOOD:
+        p = subprocess.run([exe], input=_read(stem + ".lz4"), capture_output=True)
+        assert p.returncode == 0, (stem, p.stderr)
+        _check_output(stem, p.stdout)
+    p = subprocess.run([exe], input=_read("corruptionoffset0.err"), capture_output=True)
+    assert p.returncode == 1
+    assert p.stderr.decode().strip() == "raised LZ4ADA.DATA_CORRUPTION : Corrupted Block: Offset = 0 detected."
+    p = subprocess.run([exe], input=_read("t100k.lz4")[:5000], capture_output=True)
+    assert p.returncode == 2
