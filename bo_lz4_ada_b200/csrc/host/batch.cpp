@@ -35,7 +35,8 @@ struct FramePlan {
 	uint32_t first_block = 0, n_blocks = 0;
 	uint32_t block_max = 0;
 	uint64_t dst_off = 0;      // frame base in the batch output
-	bool chained = false;      // decoded by K4
+	bool chained = false;      // linked frame: decoded by K4 as one chain
+	bool solo = false;         // independent frame with big blocks: every block is its own K4 chain (a CTA each)
 	uint32_t hash_slot = 0xffffffffu;
 };
 
@@ -195,6 +196,8 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			FramePlan &fp = b->frames[it.first_frame + f];
 			fp.dst_off = pos;
 			fp.chained = !fp.independent && fp.n_blocks > 1;
+			// a big block is ~10^5 sequences in series: give it the pipelined chain kernel (one CTA)
+			fp.solo = !fp.chained && fp.block_max >= (1u << 20);
 			fp.hash_slot = 0xffffffffu;
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
@@ -204,9 +207,18 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 				if (room < fp.block_max && i + 1 < fp.n_blocks) it.slow = true;   // tight user buffer
 				const uint64_t hist = uint64_t(i) * fp.block_max;
 				d.hist_avail = hist > 0xfffffffeull ? 0xffffffffu : uint32_t(hist);
-				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME);
+				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
 				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
+				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max) {
+					d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO;
+					lz4b200_chain c;
+					c.first_block = fp.first_block + i;
+					c.n_blocks = 1;
+					c.dst_off = d.dst_off;
+					c.dst_cap = d.dst_cap;
+					b->chains.push_back(c);
+				}
 			}
 			if (fp.chained) {
 				lz4b200_chain c;
@@ -309,7 +321,9 @@ Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			FramePlan &fp = b->frames[it.first_frame + f];
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
+				d.flags &= ~(LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
 				d.flags |= LZ4B200_BLK_CHAINED;
+				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
 				d.dst_cap = fp.block_max;
 			}
 		}

@@ -92,6 +92,19 @@ __device__ __noinline__ uint32_t quad_xxh32_prologue(const uint8_t *p, uint32_t 
 	return quad_xxh32<true, false>(p, n, lane);
 }
 
+// Ordering gate for batches of one chain that are copied by different warps of a CTA (pipelined chain
+// kernel): batch `my_batch` may read output before `out_start[d % slots]` where d = *done_upto (all
+// batches < d are final); everything else of its past becomes final once *done_upto == my_batch.
+struct BatchGate {
+	volatile uint32_t *done_upto;
+	const volatile uint32_t *out_start;   // ring: frame-relative output position where batch k starts
+	const volatile uint32_t *base_lo, *base_hi;   // ring: chain-relative start of batch k's frame
+	uint32_t my_base_lo, my_base_hi;
+	volatile uint32_t *fail;
+	uint32_t slots;
+	uint32_t my_batch;
+};
+
 constexpr int SD_STRIDE = 33;           // descriptors per block row (32 used): odd stride, no bank conflicts
 constexpr uint32_t TILE_BYTES = 1024;   // per-warp staging tile for one batch of output
 
@@ -103,9 +116,10 @@ constexpr uint32_t TILE_BYTES = 1024;   // per-warp staging tile for one batch o
 // DRAM read-modify-write each: 6 GB of DRAM reads per GiB in profiles/r01_v2b_*), matches whose
 // source lies inside the batch read it back at shared-memory latency, and the finished tile goes
 // to global memory with aligned 16-byte stores.
+template <bool GATED>
 __device__ __forceinline__ bool copy_batch(const uint8_t *__restrict__ sg, uint8_t *og, uint32_t opg,
 					   uint32_t capg, const SeqDesc *sdg, uint32_t c, int lane,
-					   uint8_t *tile, uint32_t &total)
+					   uint8_t *tile, uint32_t &total, const BatchGate *gate = nullptr)
 {
 	const bool act = static_cast<uint32_t>(lane) < c;
 	uint32_t lit_pos = 0, lit = 0, ml = 0;
@@ -191,8 +205,7 @@ __device__ __forceinline__ bool copy_batch(const uint8_t *__restrict__ sg, uint8
 	const bool simple_kind = ml <= 32 && off >= ml;
 	__syncwarp();
 	// round 1: every short, non-overlapping match that waits for nothing inside the batch
-	{
-		const bool simple = !done && dep == 0 && simple_kind;
+	auto parallel_round = [&](bool simple) {
 		if (__any_sync(FULL_MASK, simple)) {
 			const uint32_t maxml = __reduce_max_sync(FULL_MASK, simple ? ml : 0u);
 			if (simple) {
@@ -229,28 +242,72 @@ __device__ __forceinline__ bool copy_batch(const uint8_t *__restrict__ sg, uint8
 			}
 		}
 		done = done || simple;
+	};
+	if (GATED) {
+		// sources that end before the chain's final frontier may go now; the rest of this batch's
+		// past becomes final when every earlier batch has finished
+		uint32_t d = 0, fpos = 0;
+		if (lane == 0) {
+			// the ring slot of batch d is only reused once batch d is done: re-check the frontier
+			for (;;) {
+				d = *gate->done_upto;
+				if (d >= gate->my_batch) {
+					fpos = opg;
+				} else {
+					const uint32_t sl = d % gate->slots;
+					// positions are frame-relative: a frontier inside an earlier frame says nothing about mine
+					const bool same = gate->base_lo[sl] == gate->my_base_lo && gate->base_hi[sl] == gate->my_base_hi;
+					fpos = same ? gate->out_start[sl] : 0u;
+				}
+				if (d >= gate->my_batch || *gate->done_upto == d) break;
+			}
+		}
+		d = __shfl_sync(FULL_MASK, d, 0);
+		fpos = __shfl_sync(FULL_MASK, fpos, 0);
+		if (d < gate->my_batch) {
+			parallel_round(!done && dep == 0 && simple_kind && src_e <= fpos);
+			if (lane == 0) {
+				while (*gate->done_upto < gate->my_batch) __nanosleep(40);
+			}
+			__syncwarp();
+			__threadfence_block();
+		}
 	}
+	parallel_round(!done && dep == 0 && simple_kind);
 	// everything else strictly in sequence order, one match at a time by the whole warp: matches that
 	// wait for output of this batch (their source is in the tile: shared-memory latency), long and
 	// self-overlapping ones
 	uint32_t rest = __ballot_sync(FULL_MASK, !done);
-	while (rest) {
-		const int j = __ffs(rest) - 1;
-		rest &= rest - 1;
-		const uint32_t offj = __shfl_sync(FULL_MASK, off, j), mlj = __shfl_sync(FULL_MASK, ml, j);
-		const uint32_t moj = __shfl_sync(FULL_MASK, mo, j);
-		const uint32_t ssj = moj - offj;
-		uint8_t *dj = wbase + moj;
-		const uint8_t *sj = (use_tile && ssj >= opg) ? tile + pad + (ssj - opg) : og + ssj;
-		__syncwarp();
-		if (offj >= mlj) {
-			if (mlj <= 32) {
-				if (static_cast<uint32_t>(lane) < mlj) dj[lane] = sj[lane];
-			} else {
-				warp_copy<false>(dj, sj, mlj, lane);
+	if (rest) {
+		// One packed word per lane so that a single shuffle serves the common case: a short,
+		// non-overlapping match whose source and destination both live in the tile.
+		const bool quick = use_tile && simple_kind && src_s >= opg;
+		const uint32_t packed = quick ? (0x80000000u | ((mo - opg) << 17) | ((src_s - opg) << 6) | (ml - 1)) : 0u;
+		uint8_t *const tp = tile + pad;
+		while (rest) {
+			const int j = __ffs(rest) - 1;
+			rest &= rest - 1;
+			const uint32_t pk = __shfl_sync(FULL_MASK, packed, j);
+			__syncwarp();
+			if (pk & 0x80000000u) {
+				const uint32_t mlj = (pk & 63u) + 1u;
+				if (static_cast<uint32_t>(lane) < mlj) tp[((pk >> 17) & 0x3fffu) + lane] = tp[((pk >> 6) & 0x7ffu) + lane];
+				continue;
 			}
-		} else {
-			match_copy_overlap(dj, offj, mlj, lane);   // source directly in front of dj
+			const uint32_t offj = __shfl_sync(FULL_MASK, off, j), mlj = __shfl_sync(FULL_MASK, ml, j);
+			const uint32_t moj = __shfl_sync(FULL_MASK, mo, j);
+			const uint32_t ssj = moj - offj;
+			uint8_t *dj = wbase + moj;
+			const uint8_t *sj = (use_tile && ssj >= opg) ? tile + pad + (ssj - opg) : og + ssj;
+			if (offj >= mlj) {
+				if (mlj <= 32) {
+					if (static_cast<uint32_t>(lane) < mlj) dj[lane] = sj[lane];
+				} else {
+					warp_copy<false>(dj, sj, mlj, lane);
+				}
+			} else {
+				match_copy_overlap(dj, offj, mlj, lane);   // source directly in front of dj
+			}
 		}
 	}
 	__syncwarp();
@@ -315,7 +372,7 @@ __device__ __forceinline__ bool chain_block_fast(const uint8_t *__restrict__ s, 
 		if (fb) return false;
 		if (cnt == 0) break;
 		uint32_t total = 0;
-		if (!copy_batch(s, frame_out, pos, cap_abs, sd, cnt, lane, tile, total)) return false;
+		if (!copy_batch<false>(s, frame_out, pos, cap_abs, sd, cnt, lane, tile, total)) return false;
 		pos += total;
 		__syncwarp();
 	}
@@ -437,7 +494,7 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 			const uint32_t c = __shfl_sync(FULL_MASK, cnt, g);
 			if (c == 0) continue;
 			uint32_t total = 0;
-			const bool okay = copy_batch(shfl_cptr(s, g), shfl_ptr(o, g), __shfl_sync(FULL_MASK, op, g),
+			const bool okay = copy_batch<false>(shfl_cptr(s, g), shfl_ptr(o, g), __shfl_sync(FULL_MASK, op, g),
 						     __shfl_sync(FULL_MASK, cap, g), sd + g * SD_STRIDE, c, lane, tile, total);
 			if (lane == g) {
 				if (okay) op += total;

@@ -122,6 +122,246 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 	}
 }
 
+// K4 pipelined: one CTA per chain -- warp 0 walks the token chains of the chain's blocks and
+// publishes batches of 32 sequences into a shared-memory ring; warps 1..7 copy batches round-robin.
+// A big block (4 MiB = ~400 K sequences) or a linked frame is serial in its *parse*; this overlaps
+// the parse with the copies and the copies with each other (ordered through BatchGate), instead of
+// alternating both in a single warp.
+constexpr int PIPE_WARPS = 4;   // measured: 3 copiers beat 7 and 15 (the parser is the limit; idle copiers only poll)
+constexpr int PIPE_COPIERS = PIPE_WARPS - 1;
+constexpr int PIPE_SLOTS = 16;
+
+struct PipeShared {
+	SeqDesc sd[PIPE_SLOTS][32];
+	uint32_t count[PIPE_SLOTS];
+	uint32_t out_start[PIPE_SLOTS];   // frame-relative output position of the batch
+	uint32_t cap_abs[PIPE_SLOTS];
+	uint32_t frame_base_lo[PIPE_SLOTS], frame_base_hi[PIPE_SLOTS];   // chain-relative start of the batch's frame
+	uint32_t src_lo[PIPE_SLOTS], src_hi[PIPE_SLOTS];                 // block payload offset in src
+	uint32_t blk[PIPE_SLOTS];
+	uint32_t done_flag[PIPE_SLOTS];
+	uint32_t produced, done_upto, fail, end_batch, fail_block;
+};
+
+__device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void vstore(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+__global__ void __launch_bounds__(PIPE_WARPS * 32)
+decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_chains,
+			 const lz4b200_chain *__restrict__ chains, const lz4b200_blk_desc *__restrict__ desc,
+			 lz4b200_blk_status *status)
+{
+	__shared__ PipeShared ps;
+	__shared__ uint4 tiles[PIPE_WARPS][(TILE_BYTES + 32) / 16];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t c = blockIdx.x;
+	if (c >= n_chains) return;
+	const lz4b200_chain ch = chains[c];
+	uint8_t *out = dst + ch.dst_off;
+	if (threadIdx.x == 0) {
+		ps.produced = 0; ps.done_upto = 0; ps.fail = 0; ps.end_batch = 0xffffffffu; ps.fail_block = 0xffffffffu;
+	}
+	if (threadIdx.x < PIPE_SLOTS) ps.done_flag[threadIdx.x] = 0;
+	__syncthreads();
+
+	if (warp == 0) {
+		// ---------------- parser ----------------
+		uint64_t pos = 0, frame_start = 0;   // chain-relative
+		uint32_t k = 0;                      // batches published
+		bool stop = false;
+		for (uint32_t i = 0; i < ch.n_blocks && !stop; i++) {
+			const uint32_t b = ch.first_block + i;
+			const lz4b200_blk_desc d = desc[b];
+			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+			const uint64_t fpos0 = pos - frame_start;
+			const uint64_t room = ch.dst_cap - pos;
+			const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+			const uint8_t *s = src + d.src_off;
+			const bool stored = (d.flags & LZ4B200_BLK_STORED) != 0;
+			const bool ordinary = !(d.flags & LZ4B200_BLK_HASH_ONLY) && fpos0 + cap < 0xfff00000ull &&
+					      !(stored && d.src_len > cap);
+			uint32_t computed = 0, declared = 0;
+			bool okay = ordinary;
+			if (okay && (d.flags & LZ4B200_BLK_HAS_CHECKSUM)) {
+				const uint8_t *t = s + d.src_len;
+				declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+				computed = quad_xxh32_prologue(s, d.src_len, lane);
+				okay = computed == declared;
+			}
+			uint32_t fpos = static_cast<uint32_t>(fpos0);
+			if (okay && stored) {
+				// stored block (lib/lz4ada.adb:685-695): no dependencies, the parser warp copies it itself
+				warp_copy<true>(out + pos, s, d.src_len, lane);
+				fpos += d.src_len;
+			} else if (okay) {
+				uint32_t ip = 0;
+				const uint32_t n = d.src_len;
+				while (ip < n && okay) {
+					// wait for a free slot (lane 0 polls), then parse up to 32 sequences into it
+					uint32_t cnt = 0, total = 0;
+					bool fb = false;
+					// the idle lanes pull the next kilobyte of the compressed stream towards L1 so that the
+					// token chain walked by lane 0 does not pay a DRAM round trip every 128 bytes
+					if (lane >= 1 && lane <= 8 && ip + 128u * lane < n)
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(s + ip + 128u * lane));
+					if (lane == 0) {
+						// every published batch is eventually marked done (copied or skipped), so this ends
+						while (k - vload(&ps.done_upto) >= PIPE_SLOTS) __nanosleep(40);
+						SeqDesc *my = ps.sd[k % PIPE_SLOTS];
+						if (vload(&ps.fail) != 0) fb = true;   // a copier gave up: stop feeding
+						while (!fb && cnt < 32 && ip < n) {
+							const uint32_t t = ld_u8<true>(s + ip);
+							uint32_t lit = t >> 4, ml = t & 15, p = ip + 1, nxt;
+							if (lit == 15 || ml == 15) {
+								if (!parse_extended(s, n, p, lit, ml, nxt)) { fb = true; break; }
+							} else {
+								const uint32_t q = p + lit;
+								if (q + 2 <= n) { ml += 4; nxt = q + 2; }
+								else if (q == n && ml == 0) { nxt = n; }
+								else { fb = true; break; }
+							}
+							*reinterpret_cast<uint2 *>(my + cnt) = make_uint2(p, lit | (ml << 16));
+							cnt++;
+							total += lit + ml;
+							ip = nxt;
+						}
+						if (total > cap - (fpos - static_cast<uint32_t>(fpos0))) fb = true;   // exact path reports it
+						if (!fb && cnt) {
+							const uint32_t sl = k % PIPE_SLOTS;
+							ps.count[sl] = cnt;
+							ps.out_start[sl] = fpos;
+							ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
+							ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
+							ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
+							ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
+							ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
+							ps.blk[sl] = b;
+							__threadfence_block();
+							vstore(&ps.produced, k + 1);
+						}
+					}
+					fb = __shfl_sync(FULL_MASK, fb ? 1 : 0, 0) != 0;
+					cnt = __shfl_sync(FULL_MASK, cnt, 0);
+					total = __shfl_sync(FULL_MASK, total, 0);
+					ip = __shfl_sync(FULL_MASK, ip, 0);
+					if (fb || vload(&ps.fail) != 0) { okay = false; break; }
+					if (cnt) { k++; fpos += total; }
+				}
+			}
+			if (okay) {
+				// provisional: stands unless a copier gives up on one of this block's batches
+				if (lane == 0) {
+					status[b].code = LZ4B200_ST_OK;
+					status[b].out_len = fpos - static_cast<uint32_t>(fpos0);
+					status[b].err_pos = 0;
+					status[b].aux = 0;
+					status[b].xxh32_computed = computed;
+					status[b].xxh32_declared = declared;
+				}
+				pos += fpos - static_cast<uint32_t>(fpos0);
+			} else {
+				// anything out of the ordinary: drain the pipeline, then the exact routine takes over from this block
+				if (lane == 0 && vload(&ps.fail_block) == 0xffffffffu) atomicMin(&ps.fail_block, i);
+				stop = true;
+			}
+		}
+		if (lane == 0) {
+			__threadfence_block();
+			vstore(&ps.end_batch, k);
+		}
+	} else {
+		// ---------------- copiers ----------------
+		uint8_t *tile = reinterpret_cast<uint8_t *>(tiles[warp]);
+		for (uint32_t k = warp - 1;; k += PIPE_COPIERS) {
+			uint32_t go = 0;
+			if (lane == 0) {
+				for (;;) {
+					if (vload(&ps.produced) > k) { go = 1; break; }
+					if (vload(&ps.end_batch) <= k) { go = 0; break; }
+					__nanosleep(40);
+				}
+			}
+			go = __shfl_sync(FULL_MASK, go, 0);
+			if (!go) break;
+			__threadfence_block();
+			const uint32_t sl = k % PIPE_SLOTS;
+			const uint32_t cnt = ps.count[sl], ostart = ps.out_start[sl], cap_abs = ps.cap_abs[sl], blk = ps.blk[sl];
+			const uint64_t fbase = ps.frame_base_lo[sl] | (static_cast<uint64_t>(ps.frame_base_hi[sl]) << 32);
+			const uint64_t soff = ps.src_lo[sl] | (static_cast<uint64_t>(ps.src_hi[sl]) << 32);
+			// Batches of blocks before the first failing block must still be completed (they are final
+			// output); batches from the failing block on are redone by the exact routine: skip them.
+			const bool skip = blk - ch.first_block >= vload(&ps.fail_block);
+			bool okay = true;
+			if (!skip) {
+				BatchGate gate;
+				gate.done_upto = &ps.done_upto;
+				gate.out_start = ps.out_start;
+				gate.base_lo = ps.frame_base_lo;
+				gate.base_hi = ps.frame_base_hi;
+				gate.my_base_lo = ps.frame_base_lo[sl];
+				gate.my_base_hi = ps.frame_base_hi[sl];
+				gate.fail = &ps.fail;
+				gate.slots = PIPE_SLOTS;
+				gate.my_batch = k;
+				uint32_t total = 0;
+				okay = copy_batch<true>(src + soff, out + fbase, ostart, cap_abs, ps.sd[sl], cnt, lane, tile, total, &gate);
+			}
+			__syncwarp();
+			if (lane == 0) {
+				if (!okay) {
+					// which block failed first decides where the exact routine restarts
+					atomicMin(&ps.fail_block, blk - ch.first_block);
+					vstore(&ps.fail, 1);
+				}
+				__threadfence_block();
+				vstore(&ps.done_flag[sl], k + 1);
+				// advance the in-order frontier
+				uint32_t dn = vload(&ps.done_upto);
+				while (vload(&ps.done_flag[dn % PIPE_SLOTS]) == dn + 1) dn++;
+				atomicMax(&ps.done_upto, dn);
+			}
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	// ---------------- exact routine from the first block the fast path gave up on ----------------
+	const uint32_t fbk = ps.fail_block;
+	if (fbk != 0xffffffffu && warp == 0) {
+		uint64_t pos = 0, frame_start = 0;
+		bool failed = false;
+		for (uint32_t i = 0; i < ch.n_blocks; i++) {
+			const uint32_t b = ch.first_block + i;
+			const lz4b200_blk_desc d = desc[b];
+			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+			if (i < fbk) {   // finished by the pipeline
+				pos += status[b].out_len;
+				continue;
+			}
+			if (failed) {
+				if (lane == 0) {
+					status[b].code = LZ4B200_ST_NOT_RUN;
+					status[b].out_len = 0; status[b].err_pos = 0; status[b].aux = 0;
+					status[b].xxh32_computed = 0; status[b].xxh32_declared = 0;
+				}
+				continue;
+			}
+			const uint64_t fpos = pos - frame_start;
+			const uint64_t room = ch.dst_cap - pos;
+			const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+			if (d.flags & LZ4B200_BLK_SOLO) {
+				// a chain of one block taken out of an independent frame: independent semantics
+				process_block<false>(src, out + pos, d, cap, d.hist_avail, status + b, lane);
+			} else {
+				const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
+				process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
+			}
+			__syncwarp();
+			if (status[b].code != LZ4B200_ST_OK) failed = true;
+			else pos += status[b].out_len;
+		}
+	}
+}
+
 // One block against a device-resident history window (single-block path under Update).
 __global__ void __launch_bounds__(32)
 stream_block_kernel(const uint8_t *__restrict__ src, uint8_t *win, const lz4b200_blk_desc *desc,
@@ -170,7 +410,9 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 		if (fb.n_blocks) base = desc[fb.first_block].dst_off;
 		for (uint32_t i = 0; i < fb.n_blocks; i++) {
 			const uint32_t b = fb.first_block + i;
-			if (status[b].code != LZ4B200_ST_OK || desc[b].dst_off != base + len) {
+			const uint32_t fl = desc[b].flags;
+			const bool placed_by_table = !(fl & LZ4B200_BLK_CHAINED) || (fl & LZ4B200_BLK_SOLO);
+			if (status[b].code != LZ4B200_ST_OK || (placed_by_table && desc[b].dst_off != base + len)) {
 				okay = false;
 				break;
 			}
@@ -572,8 +814,17 @@ int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 {
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_chains == 0) return LZ4B200_OK;
-	const uint32_t grid = (n_chains + K1_WARPS - 1) / K1_WARPS;
-	decode_linked_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+	// LZ4B200_CHAIN_KERNEL=warp selects the one-warp-per-chain kernel (A/B comparisons, tests)
+	static const bool warp_kernel = [] {
+		const char *e = getenv("LZ4B200_CHAIN_KERNEL");
+		return e && e[0] == 'w';
+	}();
+	if (warp_kernel) {
+		const uint32_t grid = (n_chains + K1_WARPS - 1) / K1_WARPS;
+		decode_linked_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+	} else {
+		decode_chain_pipe_kernel<<<n_chains, PIPE_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+	}
 	ctx->launches++;
 	CK(cudaGetLastError());
 	return LZ4B200_OK;

@@ -66,6 +66,8 @@ typedef struct lz4b200_blk_desc {
 #define LZ4B200_BLK_HASH_ONLY     4u  /* verify checksum, do not decode (used by retries) */
 #define LZ4B200_BLK_CHAINED       8u  /* decoded in order by lz4b200_decode_linked; K1 skips it */
 #define LZ4B200_BLK_FIRST_OF_FRAME 16u /* chain kernel: a new frame starts here, history restarts */
+#define LZ4B200_BLK_SOLO          32u /* chain of one block taken from an independent frame (big blocks get a
+                                       * whole CTA): its exact path keeps independent-block semantics */
 
 /* Per-block outcome written by the kernels; the host folds these in stream
  * order into the reference's exceptions. */

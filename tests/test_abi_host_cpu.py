@@ -172,8 +172,11 @@ def test_block_table_builder(stem):
         assert bool(d.flags & 1) == stored
         assert bool(d.flags & 2) == bool(flg & 0x10)
         linked = not (flg & 0x20) and len(exp) > 1
-        assert bool(d.flags & 8) == linked            # LZ4B200_BLK_CHAINED
-        assert bool(d.flags & 16) == (i == 0)         # LZ4B200_BLK_FIRST_OF_FRAME
+        # big compressed blocks of independent frames get a CTA each (a chain of one block)
+        solo = not linked and ((data[5] >> 4) & 7) >= 6 and not stored and n >= 65536
+        assert bool(d.flags & 32) == solo             # LZ4B200_BLK_SOLO
+        assert bool(d.flags & 8) == (linked or solo)  # LZ4B200_BLK_CHAINED
+        assert bool(d.flags & 16) == (i == 0 or solo) # LZ4B200_BLK_FIRST_OF_FRAME
     ho = b.host_outcome(0)
     assert ho["exception"] == "OK" and ho["end_of_frame"] == "Yes" and ho["n_blocks"] == len(exp)
 

@@ -581,3 +581,27 @@ def test_cli_unlz4ada_b200(ctx):
     assert p.stderr.decode().strip() == "raised LZ4ADA.DATA_CORRUPTION : Corrupted Block: Offset = 0 detected."
     p = subprocess.run([exe], input=_read("t100k.lz4")[:5000], capture_output=True)
     assert p.returncode == 2
+
+
+def test_pipelined_chains_repeatable(ctx):
+    """The pipelined chain kernel (one parser warp feeding seven copier warps through a shared-memory
+    ring) orders its batches with flags, not barriers: run linked frames and big solo blocks several
+    times and demand the same exact bytes every time."""
+    text = corpus.text_like(3 << 20, seed=123)
+    rle = corpus.rle_like(1 << 20, seed=124)
+    mix = text[:900000] + rle[:300000] + text[900000:1500000] + corpus.random_bytes(100000, seed=9) + text[1500000:2500000]
+    streams, plains = [], []
+    for i in range(12):
+        p = mix[i * 1000:i * 1000 + 1500000 + i * 50000]
+        streams.append(corpus.build_frame(p, 4 + (i % 4), i % 2 == 0, True, True, independent=False))   # linked
+        plains.append(p)
+    for i in range(6):
+        p = text[i * 3000:i * 3000 + 2500000]
+        streams.append(corpus.build_frame(p, 7, False, True))                                          # solo 4 MiB blocks
+        plains.append(p)
+        streams.append(corpus.build_legacy_frame(p))                                                    # legacy 8 MiB block
+        plains.append(p)
+    for rep in range(4):
+        for plain, (exc, out, eof, msg) in zip(plains, lz.batch_decompress(ctx, streams)):
+            assert exc == "OK", msg
+            assert out == plain, rep
