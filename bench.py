@@ -56,6 +56,26 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(args):
+    """DRAM bytes (read + write) of one K1 launch from the committed `ncu --set full` capture of this
+    exact workload (profiles/r01_final_k1_ncu_full_4gib.csv); None for any other workload."""
+    if not (args.size_gib == 4.0 and args.kinds == "text" and args.block == "64k" and args.frame_mib == 1.0
+            and not args.no_block_checksum):
+        return None
+    try:
+        rd = wr = None
+        with open(os.path.join(ROOT, "profiles", "r01_final_k1_ncu_full_4gib.csv")) as f:
+            for line in f:
+                parts = line.strip().split(",")
+                if parts[0] == "dram__bytes_read.sum":
+                    rd = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6}[parts[1]]
+                if parts[0] == "dram__bytes_write.sum":
+                    wr = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6}[parts[1]]
+        return int(rd + wr) if rd is not None and wr is not None else None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -323,7 +343,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "kernel_ms": {"k1_decode_blocks": k1, "k3_xxh32_frames": float(np.mean(k3_ms)) if k3_ms else 0.0},
         "roofline": {"bound": "hbm", "kernel": "decode_blocks_v2_kernel (K1)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(k1_bytes),
                      "whole_step_frac": (k1_bytes + traffic["checksum_reread"]) / (ms_per_step / 1e3) / 1e9 / peak},
     }
