@@ -238,3 +238,17 @@ def test_gpu_paths_fail_loudly_without_device():
         while pos < len(data):
             c, out, of, ol = d.Update(data[pos:])
             pos += c
+
+
+def test_host_tools(oracle):
+    """tools/lz4ada_tools.py: xxhash32 and hdrinfo counterparts (host layer only, no GPU)."""
+    import subprocess
+    import sys
+    tool = os.path.join(ROOT, "tools", "lz4ada_tools.py")
+    data = _read("t100k.bin")
+    out = subprocess.run([sys.executable, tool, "xxhash32"], input=data, capture_output=True)
+    assert out.stdout.decode().strip() == "%08x" % oracle.xxh32(data)
+    out = subprocess.run([sys.executable, tool, "hdrinfo"], input=_read("t301k.lz4"), capture_output=True).stdout.decode()
+    assert "block max        262144" in out and "block checksum   True" in out and "block independ.  False" in out
+    out = subprocess.run([sys.executable, tool, "hdrinfo"], input=_read("corruptedmagic.err"), capture_output=True).stdout.decode()
+    assert out.strip() == MAN["error"]["corruptedmagic"]["eds"]
