@@ -330,6 +330,29 @@ __device__ __forceinline__ bool copy_batch(const uint8_t *__restrict__ sg, uint8
 	return true;
 }
 
+// One token of the fast path: ip = token position.  On success p = first literal byte, lit / ml the
+// lengths (ml = 0 for the final literal-only sequence), nxt = next token position.
+__device__ __forceinline__ bool parse_token(const uint8_t *__restrict__ s, uint32_t n, uint32_t ip, uint32_t &p,
+					    uint32_t &lit, uint32_t &ml, uint32_t &nxt)
+{
+	const uint32_t t = ld_u8<true>(s + ip);
+	lit = t >> 4;
+	ml = t & 15;
+	p = ip + 1;
+	if (lit == 15 || ml == 15) return parse_extended(s, n, p, lit, ml, nxt);
+	const uint32_t q = p + lit;
+	if (q + 2 <= n) {
+		ml += 4;
+		nxt = q + 2;
+		return true;
+	}
+	if (q == n && ml == 0) {
+		nxt = n;
+		return true;
+	}
+	return false;
+}
+
 // One block of a chain by one warp through the batch machinery (lane 0 walks the token chain).
 // Positions are relative to `frame_out` (the start of the frame's flat output), so a match may
 // reach back across block boundaries; pos advances by what the block produced.  Returns false when

@@ -127,9 +127,11 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 // A big block (4 MiB = ~400 K sequences) or a linked frame is serial in its *parse*; this overlaps
 // the parse with the copies and the copies with each other (ordered through BatchGate), instead of
 // alternating both in a single warp.
-constexpr int PIPE_WARPS = 4;   // measured: 3 copiers beat 7 and 15 (the parser is the limit; idle copiers only poll)
+constexpr int PIPE_WARPS = 8;          // 1 parser + 7 copiers (measured: 3 copiers 38.8 ms, 7 copiers 34.2 ms for 256 x 4 MiB text)
 constexpr int PIPE_COPIERS = PIPE_WARPS - 1;
-constexpr int PIPE_SLOTS = 16;
+constexpr int PIPE_SLOTS = 128;         // a whole parse window (<= 86 batches) must fit beside work in flight
+constexpr uint32_t SPEC_SEG = 256;       // compressed bytes per speculative segment (one lane each)
+constexpr uint32_t SPEC_VIS = 24;        // token positions a lane publishes for its neighbour to merge with
 
 struct PipeShared {
 	SeqDesc sd[PIPE_SLOTS][32];
@@ -140,6 +142,7 @@ struct PipeShared {
 	uint32_t src_lo[PIPE_SLOTS], src_hi[PIPE_SLOTS];                 // block payload offset in src
 	uint32_t blk[PIPE_SLOTS];
 	uint32_t done_flag[PIPE_SLOTS];
+	uint16_t vis[32][SPEC_VIS];       // speculative parse: first token positions of each lane's walk (window-relative)
 	uint32_t produced, done_upto, fail, end_batch, fail_block;
 };
 
@@ -196,8 +199,124 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 			} else if (okay) {
 				uint32_t ip = 0;
 				const uint32_t n = d.src_len;
+				uint32_t spec_backoff = 0;
 				while (ip < n && okay) {
-					// wait for a free slot (lane 0 polls), then parse up to 32 sequences into it
+					// ---- speculative parallel parse of the next window (32 segments, one lane each) ----
+					if (spec_backoff == 0 && n - ip >= 4 * SPEC_SEG) {
+						const uint32_t wbase = ip;
+						const uint32_t seg_lo = wbase + lane * SPEC_SEG;
+						const uint32_t seg_hi = seg_lo + SPEC_SEG < n ? seg_lo + SPEC_SEG : n;
+						// pass 1: walk from a guessed token start (lane 0: the true one), publish the first positions
+						uint32_t p = seg_lo, cntv = 0;
+						bool dead = seg_lo >= n;
+						while (!dead && p < seg_hi) {
+							uint32_t lp, lit, ml, nx;
+							if (!parse_token(s, n, p, lp, lit, ml, nx)) { dead = true; break; }
+							if (cntv < SPEC_VIS) ps.vis[lane][cntv] = static_cast<uint16_t>(p - wbase);
+							cntv++;
+							p = nx;
+						}
+						const uint32_t exit_pos = p;
+						const uint32_t nvis = cntv < SPEC_VIS ? cntv : SPEC_VIS;
+						__syncwarp();
+						// verification: lane j walks on from its exit until it stands on a position lane j + 1 also
+						// visited -- from there on both parse identically, so lane j + 1 is in sync from that token
+						const uint32_t nvis_next = __shfl_down_sync(FULL_MASK, nvis, 1);
+						const uint32_t lo_next = seg_lo + SPEC_SEG;
+						const bool next_exists = lane < 31 && lo_next < n;
+						uint32_t bnext = 0xffffffffu;
+						bool merged = false;
+						if (!dead) {
+							if (!next_exists || exit_pos >= n) {
+								merged = true;
+								bnext = exit_pos;
+							} else {
+								uint32_t q = exit_pos, kk = 0;
+								for (uint32_t step = 0; step < 2 * SPEC_VIS; step++) {
+									while (kk < nvis_next && wbase + ps.vis[lane + 1][kk] < q) kk++;
+									if (kk >= nvis_next) break;
+									if (wbase + ps.vis[lane + 1][kk] == q) { merged = true; bnext = q; break; }
+									uint32_t lp, lit, ml, nx;
+									if (q >= lo_next + SPEC_SEG || !parse_token(s, n, q, lp, lit, ml, nx)) break;
+									q = nx;
+								}
+							}
+						}
+						const uint32_t last_lane = (n - 1 - wbase) / SPEC_SEG < 31 ? (n - 1 - wbase) / SPEC_SEG : 31;
+						const uint32_t need_mask = last_lane >= 31 ? 0xffffffffu : ((2u << last_lane) - 1u);
+						const uint32_t ok_mask = __ballot_sync(FULL_MASK, merged);
+						bool spec_ok = (ok_mask & need_mask) == need_mask;
+						uint32_t b_start = __shfl_up_sync(FULL_MASK, bnext, 1);
+						if (lane == 0) b_start = wbase;
+						const bool mine = static_cast<uint32_t>(lane) <= last_lane;
+						// pass 2: count the true tokens of [b_start, bnext)
+						uint32_t cnt_t = 0, out_t = 0;
+						if (spec_ok && mine) {
+							uint32_t q = b_start;
+							while (q < bnext) {
+								uint32_t lp, lit, ml, nx;
+								if (!parse_token(s, n, q, lp, lit, ml, nx)) { cnt_t = 0xffffffffu; break; }
+								cnt_t++;
+								out_t += lit + ml;
+								q = nx;
+							}
+							if (cnt_t != 0xffffffffu && q != bnext) cnt_t = 0xffffffffu;
+						}
+						if (__any_sync(FULL_MASK, cnt_t == 0xffffffffu)) spec_ok = false;
+						if (spec_ok) {
+							uint32_t icnt = cnt_t, iout = out_t;
+#pragma unroll
+							for (int sh = 1; sh < 32; sh <<= 1) {
+								const uint32_t a = __shfl_up_sync(FULL_MASK, icnt, sh), bsum = __shfl_up_sync(FULL_MASK, iout, sh);
+								if (lane >= sh) { icnt += a; iout += bsum; }
+							}
+							const uint32_t tot_cnt = __shfl_sync(FULL_MASK, icnt, 31), tot_out = __shfl_sync(FULL_MASK, iout, 31);
+							const uint32_t nb = (tot_cnt + 31) / 32;
+							const uint32_t used = fpos - static_cast<uint32_t>(fpos0);
+							if (tot_out > cap - used || nb > PIPE_SLOTS - 32 || tot_cnt == 0) {
+								spec_ok = false;   // capacity: the exact path reports it; nb: never with 256-byte segments
+							} else {
+								if (lane == 0) {
+									while (k + nb - vload(&ps.done_upto) > PIPE_SLOTS) __nanosleep(40);
+								}
+								__syncwarp();
+								if (vload(&ps.fail) != 0) { okay = false; break; }
+								// pass 3: emit descriptors straight into the ring at their global sequence index
+								if (mine) {
+									uint32_t idx = icnt - cnt_t, opos = fpos + (iout - out_t), q = b_start;
+									while (q < bnext) {
+										uint32_t lp, lit, ml, nx;
+										parse_token(s, n, q, lp, lit, ml, nx);
+										const uint32_t sl = (k + (idx >> 5)) % PIPE_SLOTS;
+										*reinterpret_cast<uint2 *>(&ps.sd[sl][idx & 31]) = make_uint2(lp, lit | (ml << 16));
+										if ((idx & 31) == 0) {
+											ps.count[sl] = tot_cnt - idx < 32 ? tot_cnt - idx : 32;
+											ps.out_start[sl] = opos;
+											ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
+											ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
+											ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
+											ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
+											ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
+											ps.blk[sl] = b;
+										}
+										idx++;
+										opos += lit + ml;
+										q = nx;
+									}
+								}
+								__syncwarp();
+								__threadfence_block();
+								if (lane == 0) vstore(&ps.produced, k + nb);
+								k += nb;
+								fpos += tot_out;
+								ip = __shfl_sync(FULL_MASK, bnext, last_lane);
+								continue;
+							}
+						}
+						spec_backoff = 8;   // segments did not re-synchronise here (long literal runs): go serial for a while
+					}
+					if (spec_backoff) spec_backoff--;
+					// ---- serial: wait for a free slot (lane 0 polls), then parse up to 32 sequences into it ----
 					uint32_t cnt = 0, total = 0;
 					bool fb = false;
 					// the idle lanes pull the next kilobyte of the compressed stream towards L1 so that the
