@@ -9,6 +9,7 @@
 
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_v3.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -45,6 +46,35 @@ decode_blocks_v2_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 	const uint32_t first = (blockIdx.x * K1_WARPS + warp) * G;
 	if (first >= n_blocks) return;
 	decode_group<G>(src, dst, n_blocks, first, desc, status, sd[warp], reinterpret_cast<uint8_t *>(tiles[warp]), lane);
+}
+
+// K1 third generation (kernels_v3.cuh): a CTA per block -- eight decode warps with the block's output
+// window in shared memory, one warp hashing the payloads of the CTA's blocks.
+__global__ void __launch_bounds__(v3::CTA_THREADS, 2)
+decode_blocks_v3_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t per_cta,
+			unsigned long long *prof)
+{
+	extern __shared__ __align__(16) uint8_t v3_smem[];
+	const uint32_t first = blockIdx.x * per_cta;
+	if (first >= n_blocks) return;
+	const uint32_t cnt = n_blocks - first < per_cta ? n_blocks - first : per_cta;
+	uint32_t computed = 0, declared = 0;
+	bool want = false;
+	if (threadIdx.x >= v3::NT)
+		v3::hash_role(src, first, cnt, desc, status, computed, declared, want);
+	else
+		v3::decode_role(src, dst, n_blocks, first, cnt, desc, status, v3_smem, prof);
+	__syncthreads();
+	// Check_Checksum comes before any decoding (lib/lz4ada.adb:672-676): a wrong block checksum beats
+	// whatever the decode role reported for the block
+	if (threadIdx.x >= v3::NT && want && (threadIdx.x & 3) == 0 && computed != declared) {
+		lz4b200_blk_status *st = status + first + ((threadIdx.x & 31) >> 2);
+		st->code = LZ4B200_ST_BLOCK_CHECKSUM;
+		st->out_len = 0;
+		st->err_pos = 0;
+		st->aux = 0;
+	}
 }
 
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
@@ -682,7 +712,8 @@ struct lz4b200_ctx {
 	bool own_stream = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint64_t launches = 0;
-	int blocks_per_warp = 0;   // K1 tuning: 0 = choose from the block count, -1 = v1 kernel
+	unsigned long long *d_prof = nullptr;   // LZ4B200_PROF=1: v3 phase counters (printed by lz4b200_destroy)
+	int blocks_per_warp = 0;   // K1 tuning: 0 / 64 = v3 (a CTA per block), 1..16 = v2 with G blocks per warp, -1 = v1 kernel
 	char err[256] = "";
 };
 
@@ -731,9 +762,14 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 		const int smem = 4 * 8 * XXH_RING_STRIDE;
 		cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(decode_blocks_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v3::SMEM_BYTES));
 	}
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
+	if (const char *e = getenv("LZ4B200_PROF")) {
+		if (e[0] == '1' && cudaMalloc(&ctx->d_prof, sizeof(unsigned long long) * v3::PROF_N) == cudaSuccess)
+			cudaMemset(ctx->d_prof, 0, sizeof(unsigned long long) * v3::PROF_N);
+	}
 	*out = ctx;
 	return LZ4B200_OK;
 }
@@ -743,6 +779,17 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 	if (!ctx) return LZ4B200_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->lanes[0]);
+	if (ctx->d_prof) {
+		static const char *names[v3::PROF_N] = {"load", "parse", "scan", "emit", "match", "flush", "exact", "blocks", "windows",
+							"iters", "fallback", "batches", "rounds", "early", "gatewait", "coop"};
+		unsigned long long h[v3::PROF_N] = {};
+		cudaDeviceSynchronize();
+		cudaMemcpy(h, ctx->d_prof, sizeof h, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[lz4b200 v3 prof]");
+		for (int i = 0; i < v3::PROF_N; i++) fprintf(stderr, " %s=%llu", names[i], h[i]);
+		fprintf(stderr, "\n");
+		cudaFree(ctx->d_prof);
+	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	for (int i = 1; i < 4; i++)
@@ -781,7 +828,7 @@ int lz4b200_sync_all(lz4b200_ctx *ctx)
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
 	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
-		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16))
+		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16 && blocks_per_warp != 64))
 		return LZ4B200_ERR_ARG;
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
@@ -903,6 +950,17 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_blocks == 0) return LZ4B200_OK;
 	int g = ctx->blocks_per_warp;
+	if (g == 64) {
+		// v3 (kept selectable: measured slower than v2): up to eight blocks per CTA (one hash chain per quad), but at least ~8 waves of CTAs
+		const uint32_t slots = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 2u;
+		uint32_t per = n_blocks / (8u * slots);
+		per = per < 1 ? 1 : per > v3::MAX_NB ? v3::MAX_NB : per;
+		const uint32_t grid = (n_blocks + per - 1) / per;
+		decode_blocks_v3_kernel<<<grid, v3::CTA_THREADS, v3::SMEM_BYTES, ctx->stream>>>(src, dst, n_blocks, desc, status, per, ctx->d_prof);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return LZ4B200_OK;
+	}
 	if (g == 0) {
 		// keep at least ~16 warps per SM busy; more blocks per warp = cheaper token-chain walking
 		const uint32_t per = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u;

@@ -194,9 +194,9 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
         assert out == oout, stem
 
 
-@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16])
+@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64])
 def test_batch_k1_variants(ctx, oracle, g):
-    """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8 blocks per warp): good vectors,
+    """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8/16 blocks per warp, 64 = v3 CTA per block): good vectors,
     synthetic frames and corrupted streams must all come out exactly as the oracle says."""
     ctx.set_tuning(g)
     try:
@@ -436,7 +436,7 @@ def _py_decode(block):
     return bytes(out)
 
 
-@pytest.mark.parametrize("g", [-1, 1, 8, 16])
+@pytest.mark.parametrize("g", [-1, 1, 8, 16, 64])
 def test_k1_overlap_matrix_direct(ctx, oracle, g):
     """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
     warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
@@ -483,6 +483,114 @@ def test_k1_overlap_matrix_direct(ctx, oracle, g):
     for p in (d_src, d_dst, d_desc, d_st):
         ctx.free(p)
 
+
+
+def _run_blocks_direct(ctx, blocks, cap, g, misalign=True, flags=0):
+    """lz4b200_decode_blocks on raw blocks; returns [(code, out_len, bytes)]."""
+    stride = (cap + 64 + 255) & ~255
+    src = b"".join(blocks)
+    descs = (lz.BlkDesc * len(blocks))()
+    pos = 0
+    for i, blk in enumerate(blocks):
+        descs[i].src_off, descs[i].src_len = pos, len(blk)
+        descs[i].dst_off, descs[i].dst_cap = i * stride + ((i % 16) if misalign else 0), cap
+        descs[i].flags, descs[i].hist_avail = flags, 0
+        pos += len(blk)
+    d_src, d_dst = ctx.alloc(len(src)), ctx.alloc(stride * len(blocks))
+    d_desc, d_st = ctx.alloc(ctypes_sizeof(descs)), ctx.alloc(24 * len(blocks))
+    ctx.h2d(d_src, src)
+    ctx.h2d(d_desc, bytes(descs))
+    ctx.set_tuning(g)
+    try:
+        assert lz.lib().lz4b200_decode_blocks(ctx.handle, d_src, d_dst, len(blocks), d_desc, d_st) == 0
+    finally:
+        ctx.set_tuning(0)
+    st = ctx.d2h(d_st, 24 * len(blocks))
+    out = ctx.d2h(d_dst, stride * len(blocks))
+    res = []
+    for i in range(len(blocks)):
+        code, out_len = struct.unpack_from("<II", st, 24 * i)
+        o = descs[i].dst_off
+        res.append((code, out_len, out[o:o + out_len]))
+    for p in (d_src, d_dst, d_desc, d_st):
+        ctx.free(p)
+    return res
+
+
+def _v3_shape_blocks():
+    """Blocks aimed at the v3 kernel's machinery: several compressed windows per block, token-table
+    cuts (dense 3-byte sequences), long literal runs (inside one window, across the window edge, larger
+    than a window), long and overlapping matches, every literal / match length around 15 and 24."""
+    import ctypes
+    rng = np.random.default_rng(77)
+    blocks = []
+    # encoder-made blocks: text (one window), low-ratio text + noise (two windows), rle, short periods
+    text = corpus.text_like(65536, seed=41)
+    noisy = bytearray(text)
+    for i in range(0, 65536, 3):
+        noisy[i] = int(rng.integers(0, 256))
+    for data in (text, bytes(noisy), corpus.rle_like(65536, seed=42), text[:100], text[:33000] + bytes(noisy[:32000]),
+                 bytes(65536), (b"ab" * 40000)[:65536], corpus.random_bytes(20000, seed=3) + text[:45000]):
+        blk = corpus.compress_block(data)
+        if blk is not None and len(blk) < len(data):
+            blocks.append(blk)
+    # dense sequences: 0 literals + 4-byte matches -> 3 compressed bytes per sequence (token-table cut)
+    seed = bytes(rng.integers(0, 256, 64, dtype=np.uint8))
+    seqs = [(seed, 64, 4)]
+    for i in range(15000):
+        seqs.append((b"", int(rng.integers(1, 60)), 4))
+    blocks.append(_raw_block(seqs, b"end"))
+    # 1-literal sequences with near offsets (chains of in-batch dependencies)
+    seqs = [(seed, 3, 9)]
+    for i in range(9000):
+        seqs.append((bytes([i & 255]), int(rng.integers(1, 12)), int(rng.integers(4, 7))))
+    blocks.append(_raw_block(seqs, b""))
+    # literal and match lengths around the nibble / LIT_EMIT / 32 thresholds, far and near offsets
+    seqs = [(bytes(rng.integers(0, 256, 300, dtype=np.uint8)), 200, 40)]
+    total = 340
+    for ll in list(range(0, 40)) + [254, 255, 256, 269, 270, 271, 525, 1000]:
+        for ml in (4, 18, 19, 20, 32, 33, 34, 273, 274, 275, 600):
+            if total + ll + ml > 60000:
+                continue
+            off = int(rng.integers(1, min(total + ll, 65535) + 1))
+            seqs.append((bytes(rng.integers(0, 256, ll, dtype=np.uint8)), off, ml))
+            total += ll + ml
+    blocks.append(_raw_block(seqs, b"0123456789abcdef"))
+    # literal runs: 30000 (inside the first window), across the 33792-byte window edge, 40000 (> window: exact path)
+    for first, run in ((100, 30000), (33000, 2000), (20, 40000)):
+        pre = bytes(rng.integers(0, 4, first, dtype=np.uint8))
+        lits = bytes(rng.integers(0, 256, run, dtype=np.uint8))
+        seqs = [(pre, 1, 8)] + [(b"x", 2, 5)] * 50 + [(lits, 77, 12)] + [(b"yz", 3, 300)] * 10
+        blocks.append(_raw_block(seqs, b"fin"))
+    # one giant match per offset (RLE-like), and a match that ends the block without final literals
+    for off in (1, 2, 3, 4, 7, 16, 31, 32, 33, 100, 5000):
+        lead = bytes(rng.integers(0, 256, off + 5, dtype=np.uint8))
+        blocks.append(_raw_block([(lead, off, 65536 - len(lead) - 2)], b"zz"))
+    blocks.append(_raw_block([(b"abcdefgh", 8, 20)], b"")[:-1])   # no final token: block ends after a match
+    return blocks
+
+
+@pytest.mark.parametrize("g", [64, 8, -1])
+def test_k1_v3_shapes_direct(ctx, oracle, g):
+    """The shapes above through lz4b200_decode_blocks, compared with the pure-Python decoder (and with
+    each other across kernel generations); destinations at every 16-byte phase."""
+    blocks = _v3_shape_blocks()
+    expect = [_py_decode(b) for b in blocks]
+    assert all(len(e) <= 65536 for e in expect)
+    for (code, out_len, out), exp, blk in zip(_run_blocks_direct(ctx, blocks, 65536, g), expect, blocks):
+        assert code == 0 and out_len == len(exp), (g, len(blk), code, out_len, len(exp))
+        assert out == exp, (g, len(blk))
+
+
+def test_k1_v3_many_blocks_property(ctx):
+    """4096 text blocks of 64 KiB (eight per CTA, every hash quad busy) through the batch path:
+    output identical to the plain data and the device content checksums agree with the frames'."""
+    data = corpus.text_like(1 << 20, seed=5) * 1
+    frames = [corpus.build_frame(data[(i % 13) * 1000:] + data[:(i % 13) * 1000], 4, True, True) for i in range(64)]
+    res = lz.batch_decompress(ctx, frames)
+    for i, (exc, out, eof, msg) in enumerate(res):
+        assert exc == "OK", (i, msg)
+        assert out == data[(i % 13) * 1000:] + data[:(i % 13) * 1000], i
 
 def test_py_decoder_agrees_on_vector(oracle):
     """Sanity of the test-side helper against a golden vector (keeps _py_decode honest)."""
