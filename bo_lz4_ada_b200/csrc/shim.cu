@@ -10,6 +10,7 @@
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
 #include "kernels_v3.cuh"
+#include "kernels_v4.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -75,6 +76,20 @@ decode_blocks_v3_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 		st->err_pos = 0;
 		st->aux = 0;
 	}
+}
+
+// K1 fourth generation (kernels_v4.cuh): a warp per block (G blocks per warp, hashed together and
+// decoded in turn), parallel parse and a 4 KiB output ring per warp in shared memory.
+__global__ void __launch_bounds__(v4::WARPS * 32, 5)
+decode_blocks_v4_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t G)
+{
+	extern __shared__ __align__(16) uint8_t v4_smem[];
+	v4::WarpMem *wms = reinterpret_cast<v4::WarpMem *>(v4_smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t first = (blockIdx.x * v4::WARPS + warp) * G;
+	if (first >= n_blocks) return;
+	v4::decode_group(src, dst, n_blocks, first, G, desc, status, wms[warp], lane);
 }
 
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
@@ -763,6 +778,8 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 		cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(decode_blocks_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v3::SMEM_BYTES));
+		cudaFuncSetAttribute(decode_blocks_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(v4::WARPS * sizeof(v4::WarpMem)));
 	}
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
@@ -828,7 +845,8 @@ int lz4b200_sync_all(lz4b200_ctx *ctx)
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
 	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
-		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16 && blocks_per_warp != 64))
+		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16 && blocks_per_warp != 64 && blocks_per_warp != 40 && blocks_per_warp != 41 &&
+		     blocks_per_warp != 42 && blocks_per_warp != 44 && blocks_per_warp != 48))
 		return LZ4B200_ERR_ARG;
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
@@ -957,6 +975,21 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		per = per < 1 ? 1 : per > v3::MAX_NB ? v3::MAX_NB : per;
 		const uint32_t grid = (n_blocks + per - 1) / per;
 		decode_blocks_v3_kernel<<<grid, v3::CTA_THREADS, v3::SMEM_BYTES, ctx->stream>>>(src, dst, n_blocks, desc, status, per, ctx->d_prof);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return LZ4B200_OK;
+	}
+	if (g >= 40 && g <= 48) {
+		// v4: G blocks per warp (40 = choose: enough warps for ~4 waves of 20 warps per SM)
+		uint32_t G = static_cast<uint32_t>(g - 40);
+		if (G == 0) {
+			const uint32_t per = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 20u * 4u;
+			G = n_blocks >= 8 * per ? 8 : n_blocks >= 4 * per ? 4 : n_blocks >= 2 * per ? 2 : 1;
+		}
+		const uint32_t warps = (n_blocks + G - 1) / G;
+		const uint32_t grid = (warps + v4::WARPS - 1) / v4::WARPS;
+		decode_blocks_v4_kernel<<<grid, v4::WARPS * 32, v4::WARPS * sizeof(v4::WarpMem), ctx->stream>>>(src, dst, n_blocks, desc,
+														status, G);
 		ctx->launches++;
 		CK(cudaGetLastError());
 		return LZ4B200_OK;
