@@ -51,79 +51,135 @@ struct __align__(16) WarpMem {
 };
 static_assert(sizeof(WarpMem) % 16 == 0, "");
 
-struct Walk { uint32_t x, c, o, st; };
+struct Walk { uint32_t x, c, st; };
 
-// Token chain from window position p until it leaves [.., seg_hi), by every enabled lane at once
-// (Decompress_Sequence, lib/lz4ada.adb:737-777; lengths: Process_Variable_Length :724-735).
+constexpr uint32_t STOP = 0xffffffffu;
+
+// One token that is not the plain case (a 15 nibble, the final sequence, the window edge), out of line.
+// Returns the position of the next token, or STOP with st = W_CUT / W_BAD when the walk ends in front
+// of this token (Decompress_Sequence, lib/lz4ada.adb:737-777; lengths: Process_Variable_Length :724-735).
+__device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint32_t wlen, uint32_t last, uint32_t &st)
+{
+	const uint32_t tk = cw[p];
+	uint32_t lit = tk >> 4, q = p + 1;
+	const uint32_t stop_st = last ? W_BAD : W_CUT;
+	if (lit == 15) {
+		uint32_t b;
+		do {
+			if (q >= wlen) { st = stop_st; return STOP; }
+			b = cw[q++];
+			lit += b;
+		} while (b == 255);
+	}
+	const uint32_t e = q + lit;   // end of the literals
+	if (e > wlen) { st = stop_st; return STOP; }
+	if (last && e == wlen) {
+		// final literal-only sequence (:752-764); a match nibble here is an error
+		if (tk & 15) { st = W_BAD; return STOP; }
+		return e;
+	}
+	if (e + 2 > wlen) { st = stop_st; return STOP; }
+	uint32_t nx = e + 2;
+	if ((tk & 15) == 15) {
+		uint32_t b;
+		do {
+			if (nx >= wlen) { st = stop_st; return STOP; }
+			b = cw[nx++];
+		} while (b == 255);
+	}
+	return nx;
+}
+
+// Position of the token after the one at p (STOP + st as token_slow).  In line: no extension bytes or a
+// single one per length (literal runs < 270, matches < 274); the rest goes out of line.  Garbage chains
+// of the speculative parse read "tokens" like 'o' = 0x6f all the time, so the 15 nibbles must be cheap.
+__device__ __forceinline__ uint32_t token_next(const uint8_t *cw, uint32_t p, uint32_t wlen, uint32_t last, uint32_t &st)
+{
+	const uint32_t tk = cw[p];
+	uint32_t lit = tk >> 4, q = p + 1;
+	bool slow = false;
+	if (lit == 15) {
+		// q < wlen + 1 <= CW_BYTES: the read is inside the buffer even at the window edge
+		const uint32_t b = cw[q];
+		q++;
+		lit += b;
+		slow = b == 255;
+	}
+	uint32_t nx = q + lit + 2;
+	if ((tk & 15) == 15 && nx < wlen) {
+		const uint32_t b = cw[nx];
+		nx++;
+		slow = slow || b == 255;
+	}
+	// nx >= wlen: the window edge, the final sequence, or a 15 nibble whose extension byte was not read
+	if (slow || nx >= wlen) return token_slow(cw, p, wlen, last, st);
+	return nx;
+}
+
+// Token chain from window position p until it leaves [.., seg_hi), by every enabled lane at once.
 // The loop is warp-uniform; a lane that is done idles through the remaining iterations.
 // A sequence that needs bytes beyond the window stops the walk in front of its token: W_CUT (the
 // next window starts there), or W_BAD when the window is the block's last (truncated block).
+// EMIT: record the token positions from index idx on.
 template <bool EMIT>
-__device__ __forceinline__ Walk walk_segment(const uint8_t *cw, uint32_t p, uint32_t seg_hi, uint32_t wlen, bool last,
+__device__ __forceinline__ Walk walk_segment(const uint8_t *cw, uint32_t p, uint32_t seg_hi, uint32_t wlen, uint32_t last,
 					     bool enable, uint32_t idx, uint16_t *tokpos)
 {
 	Walk r;
-	r.c = 0; r.o = 0; r.st = W_OK;
-	bool active = enable && p < seg_hi;
-	while (__any_sync(FULL_MASK, active)) {
-		if (active) {
-			const uint32_t tk = cw[p];
-			uint32_t lit = tk >> 4, ml = tk & 15;
-			uint32_t nx = p + 3 + lit;
-			bool okay = true;
-			if (lit == 15 || ml == 15 || nx > wlen) {
-				// out of line: extensions, the final sequence, the window edge
-				uint32_t q = p + 1;
-				bool cut = false;
-				if (lit == 15) {
-					uint32_t b;
-					do {
-						if (q >= wlen) { cut = true; break; }
-						b = cw[q++];
-						lit += b;
-					} while (b == 255);
-				}
-				const uint32_t e = q + lit;
-				nx = e;
-				if (!cut) {
-					if (e > wlen) {
-						cut = true;
-					} else if (last && e == wlen) {
-						if (ml) { r.st = W_BAD; okay = false; }   // :752-764
-						ml = 0;
-					} else if (e + 2 > wlen) {
-						cut = true;
-					} else {
-						nx = e + 2;
-						if (ml == 15) {
-							uint32_t b;
-							do {
-								if (nx >= wlen) { cut = true; break; }
-								b = cw[nx++];
-								ml += b;
-							} while (b == 255);
-						}
-						ml += 4;
-					}
-				}
-				if (cut) { r.st = last ? W_BAD : W_CUT; okay = false; }
-			} else {
-				ml += 4;
-			}
-			if (okay) {
-				if (EMIT) {
-					tokpos[idx] = static_cast<uint16_t>(p);
-					idx++;
-				}
+	r.c = 0; r.st = W_OK;
+	uint32_t end = enable ? seg_hi : 0u;   // the lane is active while p < end
+	while (__any_sync(FULL_MASK, p < end)) {
+		if (p < end) {
+			uint32_t nx = token_next(cw, p, wlen, last, r.st);
+			if (nx != STOP) {
+				if (EMIT) tokpos[idx++] = static_cast<uint16_t>(p);
 				r.c++;
-				r.o += lit + ml;
 				p = nx;
+			} else {
+				end = 0;
 			}
-			active = okay && p < seg_hi;
 		}
 	}
 	r.x = p;
 	return r;
+}
+
+// Re-walk after the entry of a segment moved from g_old to g_new, for the lanes with `changed`: the
+// new chain normally joins the old one after a few tokens, and from there on exit, status and count
+// are the old ones.  Both chains advance in lock-step (always the one that is behind) until they
+// stand on the same position or have both left the segment.
+__device__ __forceinline__ void rewalk_merge(const uint8_t *cw, uint32_t g_new, uint32_t g_old, uint32_t seg_hi, uint32_t wlen,
+					     uint32_t last, bool changed, Walk &r)
+{
+	uint32_t a = g_new, b = g_old, ca = 0, cb = 0, st_a = W_OK;
+	// the old chain's tokens all lie below b_end; it ends standing on r.x
+	const uint32_t b_end = r.x < seg_hi ? r.x : seg_hi;
+	bool run = changed;
+	while (__any_sync(FULL_MASK, run)) {
+		if (run) {
+			const bool fin_a = a >= seg_hi || st_a != W_OK, fin_b = b >= b_end;
+			if (a == b) {
+				r.c = r.c - cb + ca;   // merged: exit and status stay
+				run = false;
+			} else if (fin_a && (fin_b || b > a)) {
+				// no common token: the new chain stands on its own
+				r.x = a; r.c = ca; r.st = st_a;
+				run = false;
+			} else {
+				const bool step_a = !fin_a && (a < b || fin_b);
+				const uint32_t t = step_a ? a : b;
+				uint32_t st_t = W_OK;
+				const uint32_t nx = token_next(cw, t, wlen, last, st_t);
+				if (step_a) {
+					if (nx == STOP) st_a = st_t;
+					else { a = nx; ca++; }
+				} else {
+					// the old chain parsed this token before: it cannot stop here
+					b = nx; cb++;
+				}
+			}
+		}
+	}
 }
 
 __device__ __forceinline__ uint32_t ridx(uint32_t x, uint32_t phase) { return (x + phase) & (RING - 1); }
@@ -180,30 +236,46 @@ __device__ __forceinline__ void coop_match(uint8_t *ring, uint32_t phase, const 
 }
 
 // Short non-overlapping match by one lane (ml <= 32, off >= ml): three aligned 16-byte loads from
-// the ring (young source) or from global memory (old source), a byte shift that brings the match
-// data to byte 0, a second one to the destination's word phase, then at most 3 head bytes + 8 aligned
-// words + 3 tail bytes of stores into the ring.  maxml = warp-uniform bound on ml among the callers.
-__device__ __forceinline__ void copy_simple(uint8_t *ring, uint32_t phase, const uint8_t *og, uint32_t src_s, uint32_t mo,
-					    uint32_t ml, uint32_t maxml, bool is_far, bool active)
+// the ring (young source) or from global memory (old source, issued early in the batch so that the L2
+// round trip overlaps the literal copies), a byte shift that brings the match data to byte 0, a second
+// one to the destination's word phase, then at most 3 head bytes + 8 aligned words + 3 tail bytes of
+// stores into the ring.
+struct Src48 {
+	uint4 A, B, C;
+	uint32_t m;   // byte offset of the match data inside A
+};
+
+__device__ __forceinline__ void load_far(Src48 &S, const uint8_t *og, uint32_t src_s, uint32_t ml, bool active)
+{
+	S.A = S.B = S.C = make_uint4(0, 0, 0, 0);
+	S.m = 0;
+	if (!active) return;
+	const uint8_t *sp = og + src_s;
+	S.m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(sp) & 15u);
+	const uint4 *base = reinterpret_cast<const uint4 *>(sp - S.m);
+	S.A = __ldcg(base);
+	if (S.m + ml > 16) S.B = __ldcg(base + 1);
+	if (S.m + ml > 32) S.C = __ldcg(base + 2);
+}
+
+__device__ __forceinline__ void load_near(Src48 &S, const uint8_t *ring, uint32_t phase, uint32_t src_s, uint32_t ml, bool active)
 {
 	if (!active) return;
-	uint4 A, B = make_uint4(0, 0, 0, 0), C = make_uint4(0, 0, 0, 0);
-	uint32_t m;
-	if (is_far) {
-		const uint8_t *sp = og + src_s;
-		m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(sp) & 15u);
-		const uint4 *base = reinterpret_cast<const uint4 *>(sp - m);
-		A = base[0];
-		if (m + ml > 16) B = base[1];
-		if (m + ml > 32) C = base[2];
-	} else {
-		const uint32_t r0 = ridx(src_s, phase);
-		m = r0 & 15u;
-		const uint32_t b0 = r0 - m;
-		A = *reinterpret_cast<const uint4 *>(ring + b0);
-		if (m + ml > 16) B = *reinterpret_cast<const uint4 *>(ring + ((b0 + 16) & (RING - 1)));
-		if (m + ml > 32) C = *reinterpret_cast<const uint4 *>(ring + ((b0 + 32) & (RING - 1)));
-	}
+	const uint32_t r0 = ridx(src_s, phase);
+	S.m = r0 & 15u;
+	const uint32_t b0 = r0 - S.m;
+	S.A = *reinterpret_cast<const uint4 *>(ring + b0);
+	if (S.m + ml > 16) S.B = *reinterpret_cast<const uint4 *>(ring + ((b0 + 16) & (RING - 1)));
+	if (S.m + ml > 32) S.C = *reinterpret_cast<const uint4 *>(ring + ((b0 + 32) & (RING - 1)));
+}
+
+// maxml = warp-uniform bound on ml among the calling lanes.
+__device__ __forceinline__ void store_simple(uint8_t *ring, uint32_t phase, const Src48 &S, uint32_t mo, uint32_t ml,
+					     uint32_t maxml, bool active)
+{
+	if (!active) return;
+	const uint4 A = S.A, B = S.B, C = S.C;
+	const uint32_t m = S.m;
 	unsigned long long d0 = A.x | (static_cast<unsigned long long>(A.y) << 32);
 	unsigned long long d1 = A.z | (static_cast<unsigned long long>(A.w) << 32);
 	unsigned long long d2 = B.x | (static_cast<unsigned long long>(B.y) << 32);
@@ -309,7 +381,7 @@ __device__ __noinline__ void slow_batch(uint8_t *ring, uint32_t phase, uint8_t *
 // One batch: sequences 32k .. 32k+31 of the window's token table, lane per sequence.
 // Returns false when the block needs the exact routine (offset 0, match reaching before the block).
 __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, const uint8_t *cw, const uint8_t *cwg,
-				      uint32_t k, uint32_t T, uint32_t wlen, bool last, BlockState &st, int lane)
+				      uint32_t k, uint32_t T, uint32_t wlen, bool last, uint32_t cap, BlockState &st, int lane)
 {
 	uint8_t *ring = wm.ring;
 	const uint32_t idx = k * 32 + lane;
@@ -354,7 +426,7 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 	const uint32_t B0 = st.pos;
 	const uint32_t out_pos = B0 + incl - len;
 	const uint32_t mo = out_pos + lit;
-	if (__any_sync(FULL_MASK, ml && (off == 0 || off > mo))) return false;
+	if (__any_sync(FULL_MASK, ml && (off == 0 || off > mo)) || total > cap - B0) return false;
 	if (total > BATCH_MAX) {
 		slow_batch(ring, phase, og, cwg, st, cnt, lit, ml, off, q, total, lane);
 		return true;
@@ -363,13 +435,35 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 	const uint32_t lo_wr = B0 + total > RING ? B0 + total - RING : 0u;
 	const uint32_t near_lo = st.ring_lo > lo_wr ? st.ring_lo : lo_wr;
 
+	// ---- matches, part 1: classify, and start the global loads of the old sources right away ----
+	const uint32_t src_s = mo - off;
+	const uint32_t src_e = src_s + (ml < off ? ml : off);   // self-overlap: the source ends where the match starts
+	const bool simple = ml <= 32 && off >= ml;
+	const bool is_far = ml != 0 && src_s < near_lo;          // then the whole source is in global memory
+	Src48 S;
+	load_far(S, og, src_s, ml, is_far && simple);
+
 	// ---- literals: lane per sequence up to LIT_LANE bytes, longer runs by the whole warp ----
 	const uint32_t maxlit = __reduce_max_sync(FULL_MASK, lit);
 	if (maxlit) {
-		const uint32_t lim = maxlit < LIT_LANE ? maxlit : LIT_LANE;
-		const uint32_t d = out_pos + phase;
-		for (uint32_t i = 0; i < lim; i++)
-			if (i < lit) ring[(d + i) & (RING - 1)] = cw[q + i];
+		const uint32_t d = ridx(out_pos, phase);
+		const uint8_t *sp = cw + q;
+		const uint32_t short_lit = lit < LIT_LANE ? lit : LIT_LANE;
+		if (!__any_sync(FULL_MASK, d + short_lit > RING)) {
+			uint8_t *dp = ring + d;
+#pragma unroll
+			for (int i4 = 0; i4 < static_cast<int>(LIT_LANE); i4 += 4) {
+				if (static_cast<uint32_t>(i4) < maxlit) {
+#pragma unroll
+					for (int i = i4; i < i4 + 4; i++)
+						if (static_cast<uint32_t>(i) < short_lit) dp[i] = sp[i];
+				}
+			}
+		} else {
+			// some lane's literals cross the end of the ring: masked stores
+			for (uint32_t i = 0; i < LIT_LANE && i < maxlit; i++)
+				if (i < short_lit) ring[(d + i) & (RING - 1)] = sp[i];
+		}
 		if (maxlit > LIT_LANE) {
 			uint32_t big = __ballot_sync(FULL_MASK, lit > LIT_LANE);
 			while (big) {
@@ -382,11 +476,7 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 		}
 	}
 
-	// ---- matches ----
-	const uint32_t src_s = mo - off;
-	const uint32_t src_e = src_s + (ml < off ? ml : off);   // self-overlap: the source ends where the match starts
-	const bool simple = ml <= 32 && off >= ml;
-	const bool is_far = src_s < near_lo;                     // then the whole source is in global memory
+	// ---- matches, part 2 ----
 	bool done = (ml == 0);
 	// dep = earlier sequences of this batch whose output overlaps my source
 	uint32_t dep = 0;
@@ -406,37 +496,47 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 		if (done || src_e <= B0) dep = 0;
 	}
 	__syncwarp();
-	// round A: every match that waits for nothing inside the batch -- short ones lane per sequence, all at once
-	{
-		const bool ready = !done && dep == 0;
-		const bool rs = ready && simple;
-		if (__any_sync(FULL_MASK, rs)) {
-			const uint32_t maxml = __reduce_max_sync(FULL_MASK, rs ? ml : 0u);
-			copy_simple(ring, phase, og, src_s, mo, ml, maxml, is_far, rs);
-		}
+	// parallel rounds, lane per sequence: first every short match that waits for nothing inside the batch,
+	// then -- as long as enough of them are ready at once -- those whose sources have just been completed
+	uint32_t undone = __ballot_sync(FULL_MASK, !done);
+	for (int round = 0;; round++) {
+		const bool rs = !done && simple && (dep & undone) == 0;
+		const uint32_t nrs = __popc(__ballot_sync(FULL_MASK, rs));
+		if (nrs == 0 || (round > 0 && nrs < 6)) break;
+		const uint32_t maxml = __reduce_max_sync(FULL_MASK, rs ? ml : 0u);
+		load_near(S, ring, phase, src_s, ml, rs && !is_far);
+		store_simple(ring, phase, S, mo, ml, maxml, rs);
 		done = done || rs;
+		__syncwarp();
+		undone = __ballot_sync(FULL_MASK, !done);
 	}
 	// the rest strictly in stream order, one match at a time by the whole warp: matches that wait for
 	// output of this batch (source in the ring, a few cycles away), long and self-overlapping ones.
-	// One packed word per lane serves the common case with a single shuffle.
-	uint32_t rest = __ballot_sync(FULL_MASK, !done);
+	// One packed word per lane serves the common case with a single shuffle; two matches per trip so
+	// that the second shuffle is in flight while the first match is copied.
+	uint32_t rest = undone;
 	if (rest) {
-		const bool quick = !done && simple && !is_far;
-		const uint32_t packed = quick ? (0x80000000u | ((mo - B0) << 16) | ((ml - 1) << 11) | (off & 0x7ffu)) : 0u;
-		const bool quick2 = quick && off < 0x800u;
-		const uint32_t pk_mine = quick2 ? packed : 0u;
-		while (rest) {
-			const int j = __ffs(rest) - 1;
-			rest &= rest - 1;
-			const uint32_t pk = __shfl_sync(FULL_MASK, pk_mine, j);
+		const bool quick = !done && simple && !is_far && off < 0x800u;
+		const uint32_t pk_mine = quick ? (0x80000000u | ((mo - B0) << 16) | ((ml - 1) << 11) | off) : 0u;
+		auto one = [&](uint32_t pk, int j) {
 			__syncwarp();
 			if (pk & 0x80000000u) {
 				const uint32_t moj = B0 + ((pk >> 16) & 0x7fffu), mlj = ((pk >> 11) & 31u) + 1u, offj = pk & 0x7ffu;
 				if (static_cast<uint32_t>(lane) < mlj) ring[ridx(moj + lane, phase)] = ring[ridx(moj - offj + lane, phase)];
-				continue;
+			} else {
+				coop_match(ring, phase, og, __shfl_sync(FULL_MASK, mo, j), __shfl_sync(FULL_MASK, off, j),
+					   __shfl_sync(FULL_MASK, ml, j), near_lo, lane);
 			}
-			coop_match(ring, phase, og, __shfl_sync(FULL_MASK, mo, j), __shfl_sync(FULL_MASK, off, j),
-				   __shfl_sync(FULL_MASK, ml, j), near_lo, lane);
+		};
+		while (rest) {
+			const int j1 = __ffs(rest) - 1;
+			rest &= rest - 1;
+			const bool two = rest != 0;
+			const int j2 = two ? __ffs(rest) - 1 : j1;
+			rest &= rest - 1;
+			const uint32_t pk1 = __shfl_sync(FULL_MASK, pk_mine, j1), pk2 = __shfl_sync(FULL_MASK, pk_mine, j2);
+			one(pk1, j1);
+			if (two) one(pk2, j2);
 		}
 		__syncwarp();
 	}
@@ -463,7 +563,7 @@ __device__ __forceinline__ bool decode_block(const uint8_t *__restrict__ s, uint
 		const uint8_t *g0 = s + ip;
 		const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g0) & 15u);
 		const uint32_t wlen = n - ip < WIN ? n - ip : WIN;
-		const bool last = ip + wlen == n;
+		const uint32_t last = ip + wlen == n ? 1u : 0u;
 		const uint32_t nvec = (mis + wlen + 15u) >> 4;
 		__syncwarp();
 		for (uint32_t v = lane; v < nvec; v += 32) cp_async16(wm.cw + v * 16, g0 - mis + v * 16);
@@ -477,36 +577,42 @@ __device__ __forceinline__ bool decode_block(const uint8_t *__restrict__ s, uint
 		const uint32_t seg_hi = seg_lo + SEG < wlen ? seg_lo + SEG : wlen;
 		uint32_t g = seg_lo < wlen ? seg_lo : wlen;
 		Walk r = walk_segment<false>(cw, g, seg_hi, wlen, last, true, 0, nullptr);
-		for (;;) {
+		for (uint32_t pass = 0;; pass++) {
 			uint32_t ng = __shfl_up_sync(FULL_MASK, r.x, 1);
 			if (lane == 0) ng = 0;
 			const bool changed = ng != g;
 			if (!__any_sync(FULL_MASK, changed)) break;
+			if (pass == 0) {
+				// nearly every lane moves from its guess to the true entry: plain walk
+				const Walk r2 = walk_segment<false>(cw, ng, seg_hi, wlen, last, changed, 0, nullptr);
+				if (changed) r = r2;
+			} else {
+				// a few lanes move again: follow the new chain only until it joins the old one
+				rewalk_merge(cw, ng, g, seg_hi, wlen, last, changed, r);
+			}
 			if (changed) g = ng;
-			const Walk r2 = walk_segment<false>(cw, g, seg_hi, wlen, last, changed, 0, nullptr);
-			if (changed) r = r2;
 		}
 		if (__any_sync(FULL_MASK, r.st == W_BAD)) return false;
-		// ---------------- scan: sequences and output bytes in front of every segment ----------------
-		uint32_t ic = r.c, io = r.o;
+		// ---------------- scan: sequences in front of every segment ----------------
+		uint32_t ic = r.c;
 #pragma unroll
 		for (int sft = 1; sft < 32; sft <<= 1) {
-			const uint32_t a = __shfl_up_sync(FULL_MASK, ic, sft), c2 = __shfl_up_sync(FULL_MASK, io, sft);
-			if (lane >= sft) { ic += a; io += c2; }
+			const uint32_t a = __shfl_up_sync(FULL_MASK, ic, sft);
+			if (lane >= sft) ic += a;
 		}
 		const bool use = ic <= NTOK;   // leading segments that fit the token table
 		const uint32_t nuse = __popc(__ballot_sync(FULL_MASK, use));
 		if (nuse == 0) return false;
-		const uint32_t T = __shfl_sync(FULL_MASK, ic, nuse - 1), O = __shfl_sync(FULL_MASK, io, nuse - 1);
+		const uint32_t T = __shfl_sync(FULL_MASK, ic, nuse - 1);
 		const uint32_t wend = __shfl_sync(FULL_MASK, r.x, nuse - 1);
-		if (wend == 0 || T == 0 || O > cap - st.pos) return false;
+		if (wend == 0 || T == 0) return false;
 		// ---------------- emit the token table ----------------
 		walk_segment<true>(cw, g, seg_hi, wlen, last, use && r.c != 0, ic - r.c, wm.tokpos);
 		__syncwarp();
 		// ---------------- batches ----------------
 		const uint32_t nb = (T + 31) >> 5;
 		for (uint32_t k = 0; k < nb; k++)
-			if (!batch(wm, phase, og, cw, g0, k, T, wlen, last, st, lane)) return false;
+			if (!batch(wm, phase, og, cw, g0, k, T, wlen, last != 0, cap, st, lane)) return false;
 		ip += wend;
 	}
 	flush_ring(wm.ring, phase, og, st.flushed, st.pos, lane);

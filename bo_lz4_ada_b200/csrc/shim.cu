@@ -11,6 +11,7 @@
 #include "kernels_v2.cuh"
 #include "kernels_v3.cuh"
 #include "kernels_v4.cuh"
+#include "kernels_v5.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -90,6 +91,18 @@ decode_blocks_v4_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 	const uint32_t first = (blockIdx.x * v4::WARPS + warp) * G;
 	if (first >= n_blocks) return;
 	v4::decode_group(src, dst, n_blocks, first, G, desc, status, wms[warp], lane);
+}
+
+// K1 fifth generation (kernels_v5.cuh): a LANE per block, 32 blocks in lock-step per warp, per-lane
+// rings in shared memory (bank-per-lane layout); lanes take blocks from a global counter.
+__global__ void __launch_bounds__(v5::WARPS * 32, 4)
+decode_blocks_v5_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t *counter)
+{
+	extern __shared__ __align__(16) uint8_t v5_smem[];
+	v5::WarpMem *wms = reinterpret_cast<v5::WarpMem *>(v5_smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	v5::decode_lanes(src, dst, n_blocks, desc, status, counter, wms[warp], lane);
 }
 
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
@@ -727,6 +740,7 @@ struct lz4b200_ctx {
 	bool own_stream = false;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint64_t launches = 0;
+	uint32_t *d_counter = nullptr;          // v5: block queue heads, one per lane (stream) of the context
 	unsigned long long *d_prof = nullptr;   // LZ4B200_PROF=1: v3 phase counters (printed by lz4b200_destroy)
 	int blocks_per_warp = 0;   // K1 tuning: 0 / 64 = v3 (a CTA per block), 1..16 = v2 with G blocks per warp, -1 = v1 kernel
 	char err[256] = "";
@@ -778,11 +792,14 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 		cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(decode_blocks_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v3::SMEM_BYTES));
+		cudaFuncSetAttribute(decode_blocks_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(v5::WARPS * sizeof(v5::WarpMem)));
 		cudaFuncSetAttribute(decode_blocks_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v4::WARPS * sizeof(v4::WarpMem)));
 	}
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
+	if (cudaMalloc(&ctx->d_counter, 4 * 64) != cudaSuccess) ctx->d_counter = nullptr;
 	if (const char *e = getenv("LZ4B200_PROF")) {
 		if (e[0] == '1' && cudaMalloc(&ctx->d_prof, sizeof(unsigned long long) * v3::PROF_N) == cudaSuccess)
 			cudaMemset(ctx->d_prof, 0, sizeof(unsigned long long) * v3::PROF_N);
@@ -807,6 +824,7 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 		fprintf(stderr, "\n");
 		cudaFree(ctx->d_prof);
 	}
+	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	for (int i = 1; i < 4; i++)
@@ -846,7 +864,7 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
 	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
 		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16 && blocks_per_warp != 64 && blocks_per_warp != 40 && blocks_per_warp != 41 &&
-		     blocks_per_warp != 42 && blocks_per_warp != 44 && blocks_per_warp != 48))
+		     blocks_per_warp != 42 && blocks_per_warp != 44 && blocks_per_warp != 48 && blocks_per_warp != 50))
 		return LZ4B200_ERR_ARG;
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
@@ -975,6 +993,24 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		per = per < 1 ? 1 : per > v3::MAX_NB ? v3::MAX_NB : per;
 		const uint32_t grid = (n_blocks + per - 1) / per;
 		decode_blocks_v3_kernel<<<grid, v3::CTA_THREADS, v3::SMEM_BYTES, ctx->stream>>>(src, dst, n_blocks, desc, status, per, ctx->d_prof);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return LZ4B200_OK;
+	}
+	if (g == 50) {
+		// v5: lanes pull blocks from a counter; one counter per stream lane of the context
+		if (!ctx->d_counter) return LZ4B200_ERR_NOMEM;
+		int li = 0;
+		for (int i = 0; i < 4; i++)
+			if (ctx->lanes[i] == ctx->stream) li = i;
+		uint32_t *counter = ctx->d_counter + 16 * li;
+		CK(cudaMemsetAsync(counter, 0, 4, ctx->stream));
+		const uint32_t sms = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148);
+		uint32_t warps = (n_blocks + 31) / 32;
+		if (warps > sms * 16) warps = sms * 16;
+		const uint32_t grid = (warps + v5::WARPS - 1) / v5::WARPS;
+		decode_blocks_v5_kernel<<<grid, v5::WARPS * 32, v5::WARPS * sizeof(v5::WarpMem), ctx->stream>>>(src, dst, n_blocks, desc,
+														status, counter);
 		ctx->launches++;
 		CK(cudaGetLastError());
 		return LZ4B200_OK;

@@ -194,10 +194,10 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
         assert out == oout, stem
 
 
-@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64, 40, 41, 48])
+@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64, 40, 41, 48, 50])
 def test_batch_k1_variants(ctx, oracle, g):
     """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8/16 blocks per warp, 64 = v3 CTA per block,
-    40..48 = v4 warp per block with a shared-memory ring): good vectors,
+    40..48 = v4 warp per block with a shared-memory ring, 50 = v5 lane per block): good vectors,
     synthetic frames and corrupted streams must all come out exactly as the oracle says."""
     ctx.set_tuning(g)
     try:
@@ -437,7 +437,7 @@ def _py_decode(block):
     return bytes(out)
 
 
-@pytest.mark.parametrize("g", [-1, 1, 8, 16, 64, 41, 48])
+@pytest.mark.parametrize("g", [-1, 1, 8, 16, 64, 41, 48, 50])
 def test_k1_overlap_matrix_direct(ctx, oracle, g):
     """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
     warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
@@ -571,7 +571,7 @@ def _v3_shape_blocks():
     return blocks
 
 
-@pytest.mark.parametrize("g", [64, 41, 44, 48, 8, -1])
+@pytest.mark.parametrize("g", [64, 41, 44, 48, 50, 8, -1])
 def test_k1_v3_shapes_direct(ctx, oracle, g):
     """The shapes above through lz4b200_decode_blocks, compared with the pure-Python decoder (and with
     each other across kernel generations); destinations at every 16-byte phase."""
