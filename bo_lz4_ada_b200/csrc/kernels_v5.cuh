@@ -44,6 +44,7 @@ constexpr uint32_t GIANT = 512;           // runs of this length and more are do
 struct __align__(16) WarpMem {
 	uint32_t in_w[IWW][32];
 	uint32_t out_w[OWW][32];
+	uint4 stage[32][3];   // per lane: the 48 bytes around an old match source, landed by cp.async
 };
 
 // block level
@@ -116,16 +117,9 @@ __device__ __forceinline__ void fetch_col(Bytes36 &D, const uint8_t *ringb, uint
 	for (int j = 0; j < 9; j++) D.w[j] = __funnelshift_r(x[j], x[j + 1], bs);
 }
 
-// n <= 32 bytes starting at global address p into registers (three aligned 16-byte loads).
-__device__ __forceinline__ void fetch_global(Bytes36 &D, const uint8_t *p, uint32_t n, bool active)
+// 48 aligned bytes A|B|C whose payload starts at byte m -> registers (byte 0 = payload byte 0).
+__device__ __forceinline__ void align48(Bytes36 &D, const uint4 &A, const uint4 &B, const uint4 &C, uint32_t m)
 {
-	if (!active) return;
-	const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 15u);
-	const uint4 *base = reinterpret_cast<const uint4 *>(p - m);
-	const uint4 A = __ldcg(base);
-	uint4 B = make_uint4(0, 0, 0, 0), C = make_uint4(0, 0, 0, 0);
-	if (m + n > 16) B = __ldcg(base + 1);
-	if (m + n > 32) C = __ldcg(base + 2);
 	uint32_t x0 = A.x, x1 = A.y, x2 = A.z, x3 = A.w, x4 = B.x, x5 = B.y, x6 = B.z, x7 = B.w, x8 = C.x, x9 = C.y, x10 = C.z,
 		 x11 = C.w;
 	if (m & 8) { x0 = x2; x1 = x3; x2 = x4; x3 = x5; x4 = x6; x5 = x7; x6 = x8; x7 = x9; x8 = x10; x9 = x11; x10 = 0; }
@@ -134,6 +128,34 @@ __device__ __forceinline__ void fetch_global(Bytes36 &D, const uint8_t *p, uint3
 	D.w[0] = __funnelshift_r(x0, x1, bs); D.w[1] = __funnelshift_r(x1, x2, bs); D.w[2] = __funnelshift_r(x2, x3, bs);
 	D.w[3] = __funnelshift_r(x3, x4, bs); D.w[4] = __funnelshift_r(x4, x5, bs); D.w[5] = __funnelshift_r(x5, x6, bs);
 	D.w[6] = __funnelshift_r(x6, x7, bs); D.w[7] = __funnelshift_r(x7, x8, bs); D.w[8] = __funnelshift_r(x8, x9, bs);
+}
+
+// Old match source, two halves one trip apart: issue the aligned 16-byte granules around [p, p + n) into the
+// lane's staging slot with cp.async (no registers held while the L2 / DRAM round trip is in flight) ...
+__device__ __forceinline__ void stage_issue(uint4 *slot, const uint8_t *p, uint32_t n)
+{
+	const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 15u);
+	const uint8_t *base = p - m;
+	cp_async16(slot, base);
+	if (m + n > 16) cp_async16(slot + 1, base + 16);
+	if (m + n > 32) cp_async16(slot + 2, base + 32);
+}
+// ... and pick them up after cp.async.wait_group in the next trip.
+__device__ __forceinline__ void stage_take(Bytes36 &D, const uint4 *slot, const uint8_t *p, uint32_t n, bool active)
+{
+	if (!active) return;
+	const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 15u);
+	const uint4 A = slot[0];
+	uint4 B = make_uint4(0, 0, 0, 0), C = make_uint4(0, 0, 0, 0);
+	if (m + n > 16) B = slot[1];
+	if (m + n > 32) C = slot[2];
+	align48(D, A, B, C, m);
+}
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+	const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
 }
 
 // Process_Variable_Length (lib/lz4ada.adb:724-735) for a 15 nibble: up to two extension bytes from the in
@@ -181,6 +203,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 	uint32_t computed = 0, declared = 0;
 	uint32_t rem_lit = 0, rem_ml = 0, dist = 0, mln = 0;   // the sequence in progress
 	uint32_t g_len = 0, g_off = 0;                         // a parked giant: literal run (g_off == 0) or match
+	uint32_t rf = 0;                                       // bytes of the in ring refill in flight (0 or 16)
 	bool exhausted = false;
 	uint32_t idle_trips = 0;   // trips in which no lane made progress: a safety net, never reached on valid state
 
@@ -268,6 +291,11 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			continue;
 		}
 
+		// ================= everything requested in the last trip has landed =================
+		cp_async_wait<0>();
+		a_loaded += rf;
+		rf = 0;
+
 		// ================= parked work that needs the whole warp =================
 		uint32_t coop = __ballot_sync(FULL_MASK, state == L_GIANT || state == L_EXACT);
 		while (coop) {
@@ -319,29 +347,47 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			__syncwarp();
 		}
 
-		// ================= refill the in ring: one aligned chunk per trip when there is room =================
+		// ================= the copies issued in the last trip have landed =================
 		const bool run = state == L_RUN;
 		bool bad = false, giant = false, progressed = false;
-		{
-			// a length read from global memory may have carried a_cur past the loaded chunks: skip them
-			if (a_loaded < (a_cur & ~15u)) a_loaded = a_cur & ~15u;
-			const uint32_t a_end16 = (a_end + 15u) & ~15u;
-			const bool room = run && a_loaded < a_end16 && a_loaded + 16u - (a_cur & ~15u) <= IN_BYTES;
-			if (room) {
-				progressed = true;
-				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(sbase + a_loaded));
-				const uint32_t u0 = ((a_loaded >> 2) << 7) | lane4;
-				constexpr uint32_t M = IWW * 128 - 1;
-				*reinterpret_cast<uint32_t *>(inb + ((u0 + 0) & M)) = v.x;
-				*reinterpret_cast<uint32_t *>(inb + ((u0 + 128) & M)) = v.y;
-				*reinterpret_cast<uint32_t *>(inb + ((u0 + 256) & M)) = v.z;
-				*reinterpret_cast<uint32_t *>(inb + ((u0 + 384) & M)) = v.w;
-				a_loaded += 16;
-			}
-		}
+		uint4 *slot = &wm.stage[lane][0];
 		const uint32_t have = a_loaded < a_end ? a_loaded : a_end;   // payload bytes are valid below this
 		const bool all_in = have == a_end;
 
+		// ================= stage 4: up to 32 match bytes (Output_With_History, :845-904) =================
+		// The piece was set up in an earlier trip (stage 3, or the previous piece of a long match); if its source
+		// is old, the bytes around it were requested then and are in the staging slot now.
+		Bytes36 D;
+#pragma unroll
+		for (int j = 0; j < 9; j++) D.w[j] = 0;
+		{
+			uint32_t n = 0;
+			if (run && sq == S_MATCH) {
+				n = rem_ml < ML_PIECE ? rem_ml : ML_PIECE;
+				n = n < dist ? n : dist;   // a piece never overlaps its own source
+			}
+			const uint32_t src_s = p_cur - dist;
+			// what the ring still holds once this piece is written
+			const uint32_t lo_wr = p_cur + n > OUT_BYTES ? p_cur + n - OUT_BYTES : 0u;
+			const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
+			const bool is_near = n != 0 && src_s >= near_lo;
+			const bool is_far = n != 0 && !is_near;
+			// an old source is read from global memory, up to the flush frontier (the rest follows as a young one)
+			if (is_far && p_flushed - src_s < n) n = p_flushed - src_s;
+			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
+			if (maxn) {
+				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + src_s, n, is_far);
+				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, src_s, n, maxn, is_near);
+				store_bytes(outb, lane4, D, p_cur, n, maxn, n != 0);
+				if (n) {
+					p_cur += n;
+					rem_ml -= n;
+					if (dist < ML_PIECE && n == dist) dist <<= 1;   // the pattern has doubled
+					if (rem_ml == 0) sq = S_TOKEN;
+					progressed = true;
+				}
+			}
+		}
 		// ================= stage 1: token (Decompress_Sequence, lib/lz4ada.adb:737-750) =================
 		if (run && sq == S_TOKEN) {
 			const uint32_t avail = have > a_cur ? have - a_cur : 0u;
@@ -364,7 +410,6 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			}
 		}
 		// ================= stage 2: up to 16 literal bytes, in ring -> registers -> out ring (:790-824) =================
-		Bytes36 D;
 #pragma unroll
 		for (int j = 0; j < 9; j++) D.w[j] = 0;
 		{
@@ -411,35 +456,6 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 						progressed = true;
 						if (ml >= GIANT) { giant = true; g_len = ml; g_off = off; }
 					}
-				}
-			}
-		}
-		// ================= stage 4: up to 32 match bytes (Output_With_History, :845-904) =================
-		{
-			uint32_t n = 0;
-			if (state == L_RUN && !bad && !giant && sq == S_MATCH) {
-				n = rem_ml < ML_PIECE ? rem_ml : ML_PIECE;
-				n = n < dist ? n : dist;   // a piece never overlaps its own source
-			}
-			const uint32_t src_s = p_cur - dist;
-			// what the ring still holds once this piece is written
-			const uint32_t lo_wr = p_cur + n > OUT_BYTES ? p_cur + n - OUT_BYTES : 0u;
-			const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
-			const bool is_near = n != 0 && src_s >= near_lo;
-			const bool is_far = n != 0 && !is_near;
-			// an old source is read from global memory, up to the flush frontier (the rest follows as a young one)
-			if (is_far && p_flushed - src_s < n) n = p_flushed - src_s;
-			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
-			if (maxn) {
-				if (__any_sync(FULL_MASK, is_far)) fetch_global(D, obase + src_s, n, is_far);
-				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, src_s, n, maxn, is_near);
-				store_bytes(outb, lane4, D, p_cur, n, maxn, n != 0);
-				if (n) {
-					p_cur += n;
-					rem_ml -= n;
-					if (dist < ML_PIECE && n == dist) dist <<= 1;   // the pattern has doubled
-					if (rem_ml == 0) sq = S_TOKEN;
-					progressed = true;
 				}
 			}
 		}
@@ -496,6 +512,38 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				state = L_GIANT;
 			}
 			progressed = true;
+		}
+		// ================= requests for the next trip (cp.async: no registers wait for them) =================
+		{
+			// the match piece the next trip will copy: if its source is old, fetch the bytes around it now
+			if (state == L_RUN && sq == S_MATCH && rem_ml != 0) {
+				uint32_t n = rem_ml < ML_PIECE ? rem_ml : ML_PIECE;
+				n = n < dist ? n : dist;
+				const uint32_t src_s = p_cur - dist;
+				const uint32_t lo_wr = p_cur + n > OUT_BYTES ? p_cur + n - OUT_BYTES : 0u;
+				const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
+				if (src_s < near_lo) {
+					if (p_flushed - src_s < n) n = p_flushed - src_s;
+					stage_issue(slot, obase + src_s, n);
+				}
+			}
+			// in ring: one aligned chunk per trip when there is room
+			// (a length read from global memory may have carried a_cur past the loaded chunks: skip them)
+			if (a_loaded < (a_cur & ~15u)) a_loaded = a_cur & ~15u;
+			const uint32_t a_end16 = (a_end + 15u) & ~15u;
+			const bool room = state == L_RUN && a_loaded < a_end16 && a_loaded + 16u - (a_cur & ~15u) <= IN_BYTES;
+			if (room) {
+				const uint8_t *g = sbase + a_loaded;
+				const uint32_t u0 = ((a_loaded >> 2) << 7) | lane4;
+				constexpr uint32_t M = IWW * 128 - 1;
+				cp_async4(inb + ((u0 + 0) & M), g);
+				cp_async4(inb + ((u0 + 128) & M), g + 4);
+				cp_async4(inb + ((u0 + 256) & M), g + 8);
+				cp_async4(inb + ((u0 + 384) & M), g + 12);
+				rf = 16;
+				progressed = true;
+			}
+			cp_async_commit();
 		}
 		// safety net: a state the lock-step machine cannot leave must not hang the device -- hand the blocks to the
 		// exact routine (a lane makes progress whenever it consumes input, writes output, parks or finishes)
