@@ -667,12 +667,8 @@ int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t
 	if (!nb || !b->tables_uploaded || !b->placed) return LZ4ADA_ASSERTION_ERROR;
 	if (n_chunks < 1) n_chunks = 1;
 	if (n_chunks > ni) n_chunks = uint32_t(ni);
-	// one K1 shape for all chunks: pick it from the whole batch, not from a chunk's block count
+	// K1 picks its shape per launch from the chunk's block count (lz4b200_decode_blocks, tuning 0)
 	const int saved_tuning = lz4b200_get_tuning(ctx);
-	if (saved_tuning == 0) {
-		const uint64_t per = uint64_t(lz4b200_sm_count(ctx) > 0 ? lz4b200_sm_count(ctx) : 148) * 16u;
-		lz4b200_set_tuning(ctx, nb >= 8 * per ? 8 : nb >= 4 * per ? 4 : nb >= 2 * per ? 2 : 1);
-	}
 	int rc = LZ4ADA_OK;
 	size_t chain_pos = 0, hash_pos = 0;
 	for (uint32_t c = 0; c < n_chunks && rc == LZ4ADA_OK; c++) {

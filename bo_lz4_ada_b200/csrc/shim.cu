@@ -742,7 +742,8 @@ struct lz4b200_ctx {
 	uint64_t launches = 0;
 	uint32_t *d_counter = nullptr;          // v5: block queue heads, one per lane (stream) of the context
 	unsigned long long *d_prof = nullptr;   // LZ4B200_PROF=1: v3 phase counters (printed by lz4b200_destroy)
-	int blocks_per_warp = 0;   // K1 tuning: 0 / 64 = v3 (a CTA per block), 1..16 = v2 with G blocks per warp, -1 = v1 kernel
+	int blocks_per_warp = 0;   // K1 tuning: 0 = auto (v5 for big batches, else v4), 50 = v5, 40..48 = v4, 64 = v3,
+	                           // 1..16 = v2 with G blocks per warp, -1 = v1 kernel
 	char err[256] = "";
 };
 
@@ -986,6 +987,12 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_blocks == 0) return LZ4B200_OK;
 	int g = ctx->blocks_per_warp;
+	if (g == 0) {
+		// auto: v5 (a lane per block) needs tens of thousands of blocks to fill the chip -- 148 SMs x 16 warps x 32
+		// lanes; below that v4 (a warp per block) is the faster shape
+		const uint32_t lanes = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u * 32u;
+		g = n_blocks >= lanes / 2 + lanes / 8 ? 50 : 40;
+	}
 	if (g == 64) {
 		// v3 (kept selectable: measured slower than v2): up to eight blocks per CTA (one hash chain per quad), but at least ~8 waves of CTAs
 		const uint32_t slots = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 2u;
