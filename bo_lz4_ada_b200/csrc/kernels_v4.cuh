@@ -685,8 +685,10 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 			}
 			continue;
 		}
+		// a payload that can expand more than 32-fold is a handful of giant matches (zero pages, RLE): the exact
+		// routine's warp-wide length scan and pattern replication are the right tool, skip the parse machinery
 		uint32_t produced = 0;
-		const bool okay = decode_block(sg, ng, og, capg, wm, lane, produced);
+		const bool okay = !(ng < 131072u && capg >= 65536u && ng * 32u < capg) && decode_block(sg, ng, og, capg, wm, lane, produced);
 		__syncwarp();
 		if (static_cast<uint32_t>(lane) == g) {
 			if (okay) {

@@ -873,6 +873,27 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 
 int lz4b200_get_tuning(const lz4b200_ctx *ctx) { return ctx ? ctx->blocks_per_warp : 0; }
 
+// the auto rule of lz4b200_decode_blocks, in one place
+static int k1_generation(const lz4b200_ctx *ctx, uint32_t n_blocks)
+{
+	int g = ctx->blocks_per_warp;
+	if (g == 0) {
+		// v5 (a lane per block) needs tens of thousands of blocks to fill the chip -- 148 SMs x 16 warps x 32
+		// lanes; below that v4 (a warp per block) is the faster shape
+		const uint32_t lanes = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u * 32u;
+		g = n_blocks >= lanes / 2 + lanes / 8 ? 50 : 40;
+	}
+	return g;
+}
+
+const char *lz4b200_k1_kernel_name(const lz4b200_ctx *ctx, uint32_t n_blocks)
+{
+	if (!ctx) return "";
+	const int g = k1_generation(ctx, n_blocks);
+	return g == 50 ? "decode_blocks_v5_kernel" : g >= 40 && g <= 48 ? "decode_blocks_v4_kernel" : g == 64 ? "decode_blocks_v3_kernel"
+	       : g < 0 ? "decode_blocks_kernel" : "decode_blocks_v2_kernel";
+}
+
 int lz4b200_alloc(lz4b200_ctx *ctx, size_t bytes, void **dev_ptr)
 {
 	if (!ctx || !dev_ptr) return LZ4B200_ERR_ARG;
@@ -986,13 +1007,7 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 {
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_blocks == 0) return LZ4B200_OK;
-	int g = ctx->blocks_per_warp;
-	if (g == 0) {
-		// auto: v5 (a lane per block) needs tens of thousands of blocks to fill the chip -- 148 SMs x 16 warps x 32
-		// lanes; below that v4 (a warp per block) is the faster shape
-		const uint32_t lanes = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u * 32u;
-		g = n_blocks >= lanes / 2 + lanes / 8 ? 50 : 40;
-	}
+	int g = k1_generation(ctx, n_blocks);
 	if (g == 64) {
 		// v3 (kept selectable: measured slower than v2): up to eight blocks per CTA (one hash chain per quad), but at least ~8 waves of CTAs
 		const uint32_t slots = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 2u;

@@ -133,12 +133,23 @@ int lz4b200_sm_count(const lz4b200_ctx *ctx);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx);
 
-/* K1 tuning: how many independent blocks one warp decodes side by side (1, 2, 4 or 8; their
- * token chains advance together, one lane each).  0 = pick from the block count (default),
- * -1 = the one-warp-per-block kernel that is also the exact fallback. */
+/* K1 tuning: which generation of the independent-block kernel lz4b200_decode_blocks launches.
+ *    0        choose from the block count (default): v5 when the batch fills the chip (about 47 000
+ *             blocks on a 148-SM part), v4 otherwise
+ *   50        v5: one lane per block, 32 blocks in lock-step per warp, per-lane shared-memory rings
+ *   40        v4: one warp per block, warp-parallel parse, 4 KiB shared-memory output ring per warp;
+ *             41 / 42 / 44 / 48 fix the number of blocks a warp hashes together and decodes in turn
+ *   64        v3: one CTA per block, whole output window in shared memory (kept for A/B: slow)
+ *   1..16     v2: that many blocks side by side per warp, output assembled in global memory
+ *   -1        v1: one warp per block, every lane in lock-step; also the exact fallback of all others
+ * All of them produce identical bytes and statuses (tests/test_gpu_parity.py runs every one). */
 int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp);
 
 int lz4b200_get_tuning(const lz4b200_ctx *ctx);
+
+/* Name of the kernel lz4b200_decode_blocks would launch for n_blocks under the current tuning
+ * (for logs and benchmark records). */
+const char *lz4b200_k1_kernel_name(const lz4b200_ctx *ctx, uint32_t n_blocks);
 
 /* A context owns up to four CUDA streams ("lanes"; lane 0 is the primary one given to / made by
  * lz4b200_create).  Every call enqueues on the lane selected last.  The batch scheduler uses them

@@ -54,17 +54,22 @@ def run_case(ctx, name, streams, plains, steps=3):
 
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    only = sys.argv[2] if len(sys.argv) > 2 else ""   # substring filter on the config name
     torch.cuda.set_device(0)
     ctx = lz.DeviceContext(0, torch.cuda.current_stream().cuda_stream)
     results = []
     # configs[2]: 4 MiB independent blocks, thirds RLE / text / random, one-block frames (lz4 CLI defaults:
     # content checksum, no block checksum)
     for kinds in (("rle",), ("random",), ("text",), ("rle", "text", "random")):
+        if only and only not in "4MiB-blocks/" + "+".join(kinds):
+            continue
         n = int(1024 * scale) if kinds != ("text",) else int(256 * scale)
         c = corpus.build_corpus(n * (4 << 20), 4 << 20, 7, kinds=kinds, block_checksum=False, keep_plain=True)
         streams = [bytes(c["src"][o:o + l]) for o, l in c["items"]]
         results.append(run_case(ctx, "4MiB-blocks/" + "+".join(kinds), streams, c["plain"]))
         del c, streams
+    if only:
+        return
     # configs[3]: legacy frames, concatenated modern frames, skippable frames: batch of 1024 streams
     text = corpus.text_like(6 << 20, seed=5)
     rle = corpus.rle_like(2 << 20, seed=6)
