@@ -158,22 +158,30 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
 }
 
-// Process_Variable_Length (lib/lz4ada.adb:724-735) for a 15 nibble: up to two extension bytes from the in
-// ring, anything longer (>= 525) from global memory.  q = position of the first extension byte on entry,
-// of the byte after the last one on return.  false = the block ends inside the length.
-__device__ __forceinline__ bool length_ext(const uint8_t *inb, uint32_t lane4, const uint8_t *sbase, uint32_t &q, uint32_t a_end,
-					   uint32_t &len)
+// Four bytes at position x of the lane's in ring (byte 0 = position x): two word reads and a funnel shift.
+__device__ __forceinline__ uint32_t peek32(const uint8_t *inb, uint32_t lane4, uint32_t x)
+{
+	constexpr uint32_t M = IWW * 128 - 1;
+	const uint32_t u = (((x >> 2) << 7) | lane4) & M;
+	const uint32_t w0 = *reinterpret_cast<const uint32_t *>(inb + u);
+	const uint32_t w1 = *reinterpret_cast<const uint32_t *>(inb + ((u + 128) & M));
+	return __funnelshift_r(w0, w1, (x & 3u) * 8u);
+}
+
+// Process_Variable_Length (lib/lz4ada.adb:724-735) for a 15 nibble: e1 / e2 = the first two extension bytes
+// (already read from the in ring), anything longer (>= 525) continues in global memory.  q = position of the
+// first extension byte on entry, of the byte after the last one on return.  false = the block ends inside.
+__device__ __forceinline__ bool length_ext(uint32_t e1, uint32_t e2, const uint8_t *sbase, uint32_t &q, uint32_t a_end, uint32_t &len)
 {
 	if (q >= a_end) return false;
-	uint32_t b = inb[col<IWW>(q, lane4)];
 	q++;
-	len += b;
-	if (b != 255) return true;
+	len += e1;
+	if (e1 != 255) return true;
 	if (q >= a_end) return false;
-	b = inb[col<IWW>(q, lane4)];
 	q++;
-	len += b;
-	if (b != 255) return true;
+	len += e2;
+	if (e2 != 255) return true;
+	uint32_t b;
 	do {
 		if (q >= a_end) return false;
 		b = __ldg(sbase + q);
@@ -394,11 +402,12 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			if (a_cur >= a_end) {
 				state = L_FINISH;   // the block ends after a match, or is empty
 			} else if (avail >= 3 || all_in) {
-				const uint32_t tk = inb[col<IWW>(a_cur, lane4)];
+				const uint32_t pk = peek32(inb, lane4, a_cur);   // token and two possible extension bytes
+				const uint32_t tk = pk & 255u;
 				uint32_t lit = tk >> 4;
 				mln = tk & 15u;
 				uint32_t q = a_cur + 1;
-				if (lit == 15 && !length_ext(inb, lane4, sbase, q, a_end, lit)) bad = true;
+				if (lit == 15 && !length_ext((pk >> 8) & 255u, (pk >> 16) & 255u, sbase, q, a_end, lit)) bad = true;
 				if (!bad && (lit > a_end - q || lit > p_cap - p_cur)) bad = true;
 				if (!bad) {
 					a_cur = q;
@@ -443,9 +452,10 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				if (a_cur + 2 > a_end) {
 					bad = true;
 				} else {
-					const uint32_t off = inb[col<IWW>(a_cur, lane4)] | (static_cast<uint32_t>(inb[col<IWW>(a_cur + 1, lane4)]) << 8);
+					const uint32_t pk = peek32(inb, lane4, a_cur);   // offset and two possible extension bytes
+					const uint32_t off = pk & 0xffffu;
 					uint32_t q = a_cur + 2, ml = mln;
-					if (ml == 15 && !length_ext(inb, lane4, sbase, q, a_end, ml)) bad = true;
+					if (ml == 15 && !length_ext((pk >> 16) & 255u, pk >> 24, sbase, q, a_end, ml)) bad = true;
 					ml += 4;
 					if (!bad && (off == 0 || off > p_cur - p_start || ml > p_cap - p_cur)) bad = true;
 					if (!bad) {
@@ -461,33 +471,55 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		}
 		if (bad) state = L_EXACT;   // the exact routine re-decodes the block and reports the error
 
-		// ================= flush complete 16-byte chunks of the out ring =================
+		// ================= flush the out ring: 32 bytes (two aligned 16-byte stores) at a time =================
+		auto flush16 = [&]() {
+			const uint32_t u0 = ((p_flushed >> 2) << 7) | lane4;
+			constexpr uint32_t M = OWW * 128 - 1;
+			uint4 v;
+			v.x = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 0) & M));
+			v.y = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 128) & M));
+			v.z = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 256) & M));
+			v.w = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 384) & M));
+			if (p_flushed >= p_start) {
+				*reinterpret_cast<uint4 *>(obase + p_flushed) = v;
+			} else {
+				// the block's first chunk starts in the middle of a 16-byte granule: bytes only
+				const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (int k = 0; k < 16; k++)
+					if (p_flushed + k >= p_start) obase[p_flushed + k] = static_cast<uint8_t>(ws[k >> 2] >> (8 * (k & 3)));
+			}
+			p_flushed += 16;
+		};
 #pragma unroll 1
 		for (int rep = 0; rep < 3; rep++) {
-			const bool fl = (state == L_RUN || state == L_FINISH) && (p_cur & ~15u) > p_flushed;
+			const bool fl = (state == L_RUN || state == L_FINISH) && p_cur - p_flushed >= 32u;
 			if (!__any_sync(FULL_MASK, fl)) break;
 			if (fl) {
-				const uint32_t u0 = ((p_flushed >> 2) << 7) | lane4;
-				constexpr uint32_t M = OWW * 128 - 1;
-				uint4 v;
-				v.x = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 0) & M));
-				v.y = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 128) & M));
-				v.z = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 256) & M));
-				v.w = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 384) & M));
-				if (p_flushed >= p_start) {
-					*reinterpret_cast<uint4 *>(obase + p_flushed) = v;
+				if (p_flushed < p_start) {
+					flush16();
 				} else {
-					// the block's first chunk starts in the middle of a 16-byte granule: bytes only
-					const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-					for (int k = 0; k < 16; k++)
-						if (p_flushed + k >= p_start) obase[p_flushed + k] = static_cast<uint8_t>(ws[k >> 2] >> (8 * (k & 3)));
+					const uint32_t u0 = ((p_flushed >> 2) << 7) | lane4;
+					constexpr uint32_t M = OWW * 128 - 1;
+					uint4 v, w;
+					v.x = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 0) & M));
+					v.y = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 128) & M));
+					v.z = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 256) & M));
+					v.w = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 384) & M));
+					w.x = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 512) & M));
+					w.y = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 640) & M));
+					w.z = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 768) & M));
+					w.w = *reinterpret_cast<const uint32_t *>(outb + ((u0 + 896) & M));
+					*reinterpret_cast<uint4 *>(obase + p_flushed) = v;
+					*reinterpret_cast<uint4 *>(obase + p_flushed + 16) = w;
+					p_flushed += 32;
 				}
-				p_flushed += 16;
 			}
 		}
-		// ---- a lane that parks or finishes writes the partial chunk too: global memory is then complete ----
-		if ((state == L_RUN && giant) || (state == L_FINISH && (p_cur & ~15u) <= p_flushed)) {
+		// ---- a lane that parks or finishes writes what is left, whole chunks and the partial one:
+		//      global memory is then complete ----
+		if ((state == L_RUN && giant) || (state == L_FINISH && p_cur - p_flushed < 32u)) {
+			while ((p_cur & ~15u) > p_flushed) flush16();
 			const uint32_t base16 = p_flushed;
 			if (p_cur > base16) {
 				const uint32_t u0 = ((base16 >> 2) << 7) | lane4;
