@@ -212,6 +212,11 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 	uint32_t rem_lit = 0, rem_ml = 0, dist = 0, mln = 0;   // the sequence in progress
 	uint32_t g_len = 0, g_off = 0;                         // a parked giant: literal run (g_off == 0) or match
 	uint32_t rf = 0;                                       // bytes of the in ring refill in flight (0 or 16)
+	// the match piece in flight: set up (and, for an old source, requested) at the end of one trip, copied at the
+	// end of the next one, so that the memory round trip overlaps that trip's parsing, literals and flush.
+	// p_cur already counts it; its n bytes at pend_dst are a hole until then.
+	uint32_t pend_n = 0, pend_dst = 0, pend_src = 0;
+	bool pend_far = false;
 	bool exhausted = false;
 	uint32_t idle_trips = 0;   // trips in which no lane made progress: a safety net, never reached on valid state
 
@@ -253,6 +258,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 						computed = declared = 0;
 						sq = S_TOKEN;
 						rem_lit = rem_ml = 0;
+						pend_n = 0;
 						// positions are 32-bit with headroom; odd blocks go to the exact routine
 						const bool plain = !(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_HASH_ONLY)) && d.dst_cap < 0x7fff0000u &&
 								   d.src_len < 0x7fff0000u;
@@ -299,13 +305,14 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			continue;
 		}
 
-		// ================= everything requested in the last trip has landed =================
-		cp_async_wait<0>();
-		a_loaded += rf;
-		rf = 0;
-
 		// ================= parked work that needs the whole warp =================
 		uint32_t coop = __ballot_sync(FULL_MASK, state == L_GIANT || state == L_EXACT);
+		if (coop) {
+			// (rare) the refills in flight must have landed before a lane restarts its in ring
+			cp_async_wait<0>();
+			a_loaded += rf;
+			rf = 0;
+		}
 		while (coop) {
 			const int j = __ffs(coop) - 1;
 			coop &= coop - 1;
@@ -355,47 +362,15 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			__syncwarp();
 		}
 
-		// ================= the copies issued in the last trip have landed =================
 		const bool run = state == L_RUN;
 		bool bad = false, giant = false, progressed = false;
 		uint4 *slot = &wm.stage[lane][0];
 		const uint32_t have = a_loaded < a_end ? a_loaded : a_end;   // payload bytes are valid below this
 		const bool all_in = have == a_end;
 
-		// ================= stage 4: up to 32 match bytes (Output_With_History, :845-904) =================
-		// The piece was set up in an earlier trip (stage 3, or the previous piece of a long match); if its source
-		// is old, the bytes around it were requested then and are in the staging slot now.
 		Bytes36 D;
 #pragma unroll
 		for (int j = 0; j < 9; j++) D.w[j] = 0;
-		{
-			uint32_t n = 0;
-			if (run && sq == S_MATCH) {
-				n = rem_ml < ML_PIECE ? rem_ml : ML_PIECE;
-				n = n < dist ? n : dist;   // a piece never overlaps its own source
-			}
-			const uint32_t src_s = p_cur - dist;
-			// what the ring still holds once this piece is written
-			const uint32_t lo_wr = p_cur + n > OUT_BYTES ? p_cur + n - OUT_BYTES : 0u;
-			const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
-			const bool is_near = n != 0 && src_s >= near_lo;
-			const bool is_far = n != 0 && !is_near;
-			// an old source is read from global memory, up to the flush frontier (the rest follows as a young one)
-			if (is_far && p_flushed - src_s < n) n = p_flushed - src_s;
-			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
-			if (maxn) {
-				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + src_s, n, is_far);
-				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, src_s, n, maxn, is_near);
-				store_bytes(outb, lane4, D, p_cur, n, maxn, n != 0);
-				if (n) {
-					p_cur += n;
-					rem_ml -= n;
-					if (dist < ML_PIECE && n == dist) dist <<= 1;   // the pattern has doubled
-					if (rem_ml == 0) sq = S_TOKEN;
-					progressed = true;
-				}
-			}
-		}
 		// ================= stage 1: token (Decompress_Sequence, lib/lz4ada.adb:737-750) =================
 		if (run && sq == S_TOKEN) {
 			const uint32_t avail = have > a_cur ? have - a_cur : 0u;
@@ -491,9 +466,10 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			}
 			p_flushed += 16;
 		};
+		const uint32_t p_solid = pend_n ? pend_dst : p_cur;   // output is complete below this position
 #pragma unroll 1
 		for (int rep = 0; rep < 3; rep++) {
-			const bool fl = (state == L_RUN || state == L_FINISH) && p_cur - p_flushed >= 32u;
+			const bool fl = (state == L_RUN || state == L_FINISH) && p_solid - p_flushed >= 32u && p_solid > p_flushed;
 			if (!__any_sync(FULL_MASK, fl)) break;
 			if (fl) {
 				if (p_flushed < p_start) {
@@ -515,6 +491,23 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 					p_flushed += 32;
 				}
 			}
+		}
+		// ================= everything requested in the last trip has landed =================
+		cp_async_wait<0>();
+		a_loaded += rf;
+		rf = 0;
+		// ================= stage 4: the match piece in flight, <= 32 bytes (Output_With_History, :845-904) =================
+		{
+			const uint32_t n = (state == L_EXACT) ? 0u : pend_n;
+			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
+			if (maxn) {
+				const bool is_far = n != 0 && pend_far, is_near = n != 0 && !pend_far;
+				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + pend_src, n, is_far);
+				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, pend_src, n, maxn, is_near);
+				store_bytes(outb, lane4, D, pend_dst, n, maxn, n != 0);
+				if (n) progressed = true;
+			}
+			pend_n = 0;
 		}
 		// ---- a lane that parks or finishes writes what is left, whole chunks and the partial one:
 		//      global memory is then complete ----
@@ -547,17 +540,30 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		}
 		// ================= requests for the next trip (cp.async: no registers wait for them) =================
 		{
-			// the match piece the next trip will copy: if its source is old, fetch the bytes around it now
+			// set up the next match piece (copied at the end of the next trip); an old source is requested now
 			if (state == L_RUN && sq == S_MATCH && rem_ml != 0) {
 				uint32_t n = rem_ml < ML_PIECE ? rem_ml : ML_PIECE;
-				n = n < dist ? n : dist;
+				n = n < dist ? n : dist;   // a piece never overlaps its own source
 				const uint32_t src_s = p_cur - dist;
-				const uint32_t lo_wr = p_cur + n > OUT_BYTES ? p_cur + n - OUT_BYTES : 0u;
+				// what the ring still holds when the piece is copied: the next trip may write up to 16 literal bytes
+				// behind it first
+				const uint32_t hi = p_cur + n + LIT_PIECE;
+				const uint32_t lo_wr = hi > OUT_BYTES ? hi - OUT_BYTES : 0u;
 				const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
-				if (src_s < near_lo) {
+				pend_far = src_s < near_lo;
+				if (pend_far) {
+					// read from global memory, up to the flush frontier (the rest follows as a young source)
 					if (p_flushed - src_s < n) n = p_flushed - src_s;
 					stage_issue(slot, obase + src_s, n);
 				}
+				pend_n = n;
+				pend_dst = p_cur;
+				pend_src = src_s;
+				p_cur += n;
+				rem_ml -= n;
+				if (dist < ML_PIECE && n == dist) dist <<= 1;   // the pattern has doubled
+				if (rem_ml == 0) sq = S_TOKEN;
+				progressed = true;
 			}
 			// in ring: one aligned chunk per trip when there is room
 			// (a length read from global memory may have carried a_cur past the loaded chunks: skip them)
