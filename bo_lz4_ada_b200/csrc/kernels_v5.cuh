@@ -33,7 +33,7 @@
 namespace lz4b200 {
 namespace v5 {
 
-constexpr int WARPS = 4;                  // per CTA
+constexpr int WARPS = 2;                  // per CTA: small CTAs spread a batch that does not fill the chip evenly
 constexpr uint32_t IWW = 32;              // in ring: words per lane (128 bytes)
 constexpr uint32_t OWW = 64;              // out ring: words per lane (256 bytes)
 constexpr uint32_t IN_BYTES = IWW * 4, OUT_BYTES = OWW * 4;

@@ -95,7 +95,7 @@ decode_blocks_v4_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 
 // K1 fifth generation (kernels_v5.cuh): a LANE per block, 32 blocks in lock-step per warp, per-lane
 // rings in shared memory (bank-per-lane layout); lanes take blocks from a global counter.
-__global__ void __launch_bounds__(v5::WARPS * 32, 4)
+__global__ void __launch_bounds__(v5::WARPS * 32, 8)
 decode_blocks_v5_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
 			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t *counter)
 {
