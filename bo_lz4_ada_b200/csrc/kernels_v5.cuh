@@ -23,8 +23,10 @@
 //             that one copy in global memory with the v1 warp copies, then the lane re-seeds its rings
 //
 // Lanes fetch new blocks from a global counter when enough of them are idle, so unequal blocks do not
-// leave lanes parked.  Block checksums (Check_Checksum, lib/lz4ada.adb:698-707): the quads of the warp
-// hash the newly fetched blocks, eight at a time, before they are decoded.
+// leave lanes parked.  Block checksums (Check_Checksum, lib/lz4ada.adb:698-707) are fused into the pass over
+// the compressed bytes: every lane folds each 16-byte stripe of its payload into its own XXH32 state straight
+// out of the in ring, one stripe per trip, as the chunks arrive -- the payload is read from memory once.
+// (A block with a giant skips parts of the in ring; its checksum is redone by a quad of the warp at the end.)
 // Anything unusual goes to process_block (exact error semantics of lib/lz4ada.adb:716-904).
 #pragma once
 
@@ -48,7 +50,9 @@ struct __align__(16) WarpMem {
 };
 
 // block level
-enum : uint32_t { L_IDLE = 0, L_RUN = 1, L_GIANT = 2, L_EXACT = 3, L_FINISH = 4 };
+enum : uint32_t { L_IDLE = 0, L_RUN = 1, L_GIANT = 2, L_EXACT = 3, L_FINISH = 4, L_HASH = 5 };
+// block checksum of the lane's block
+enum : uint32_t { H_NONE = 0, H_INLINE = 1, H_REDO = 2 };
 // sequence level (while L_RUN)
 enum : uint32_t { S_TOKEN = 0, S_LIT = 1, S_OFF = 2, S_MATCH = 3 };
 
@@ -168,6 +172,24 @@ __device__ __forceinline__ uint32_t peek32(const uint8_t *inb, uint32_t lane4, u
 	return __funnelshift_r(w0, w1, (x & 3u) * 8u);
 }
 
+// One 16-byte stripe at position x of the lane's in ring into the four XXH32 accumulators (Rot_Mul, :982-985).
+__device__ __forceinline__ void hash_stripe(const uint8_t *inb, uint32_t lane4, uint32_t x, uint32_t &a0, uint32_t &a1, uint32_t &a2,
+					    uint32_t &a3)
+{
+	constexpr uint32_t M = IWW * 128 - 1;
+	const uint32_t u = ((x >> 2) << 7) | lane4;
+	const uint32_t bs = (x & 3u) * 8u;
+	const uint32_t w0 = *reinterpret_cast<const uint32_t *>(inb + (u & M));
+	const uint32_t w1 = *reinterpret_cast<const uint32_t *>(inb + ((u + 128) & M));
+	const uint32_t w2 = *reinterpret_cast<const uint32_t *>(inb + ((u + 256) & M));
+	const uint32_t w3 = *reinterpret_cast<const uint32_t *>(inb + ((u + 384) & M));
+	const uint32_t w4 = *reinterpret_cast<const uint32_t *>(inb + ((u + 512) & M));
+	a0 = xxh_round(a0, __funnelshift_r(w0, w1, bs));
+	a1 = xxh_round(a1, __funnelshift_r(w1, w2, bs));
+	a2 = xxh_round(a2, __funnelshift_r(w2, w3, bs));
+	a3 = xxh_round(a3, __funnelshift_r(w3, w4, bs));
+}
+
 // Process_Variable_Length (lib/lz4ada.adb:724-735) for a 15 nibble: e1 / e2 = the first two extension bytes
 // (already read from the in ring), anything longer (>= 525) continues in global memory.  q = position of the
 // first extension byte on entry, of the byte after the last one on return.  false = the block ends inside.
@@ -208,9 +230,11 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 	uint8_t *obase = dst;          // 16-byte aligned: output byte at position x is obase[x]
 	uint32_t a_cur = 0, a_end = 0, a_loaded = 0;
 	uint32_t p_cur = 0, p_start = 0, p_cap = 0, p_flushed = 0, ring_lo = 0;
-	uint32_t computed = 0, declared = 0;
-	uint32_t rem_lit = 0, rem_ml = 0, dist = 0, mln = 0;   // the sequence in progress
-	uint32_t g_len = 0, g_off = 0;                         // a parked giant: literal run (g_off == 0) or match
+	uint32_t declared = 0;
+	uint32_t rem_lit = 0, rem_ml = 0, dist = 0, mln = 0;   // the sequence in progress; a parked giant is the literal
+	                                                       // run rem_lit (sq == S_LIT) or the match rem_ml / dist
+	// fused block checksum (XXHash32.Process, lib/lz4ada.adb:979-991): four accumulators, next stripe at h_pos
+	uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, h_pos = 0, a_beg = 0, h_mode = H_NONE;
 	uint32_t rf = 0;                                       // bytes of the in ring refill in flight (0 or 16)
 	// the match piece in flight: set up (and, for an old source, requested) at the end of one trip, copied at the
 	// end of the next one, so that the memory round trip overlaps that trip's parsing, literals and flush.
@@ -255,7 +279,9 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 						p_cap = oph + d.dst_cap;
 						p_flushed = 0;   // chunk 0 is partial when oph != 0: flushed bytewise
 						ring_lo = oph;
-						computed = declared = 0;
+						declared = 0;
+						a_beg = h_pos = mis;
+						acc0 = PRIME_1 + PRIME_2; acc1 = PRIME_2; acc2 = 0; acc3 = 0u - PRIME_1;   // Reset, :932-940
 						sq = S_TOKEN;
 						rem_lit = rem_ml = 0;
 						pend_n = 0;
@@ -266,37 +292,11 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 					}
 				}
 			}
-			// ---- block checksums of the fresh blocks: quad q hashes the q-th of them, eight per round ----
-			uint32_t todo = __ballot_sync(FULL_MASK, fresh && (hflags & LZ4B200_BLK_HAS_CHECKSUM) && state == L_RUN);
-			while (todo) {
-				uint32_t mine = __fns(todo, 0, (lane >> 2) + 1);   // the q-th set bit of todo
-				if (mine > 31) mine = 32;
-				const int srcl = mine < 32 ? static_cast<int>(mine) : 0;
-				const uint8_t *sp = shfl_cptr(hs, srcl);
-				const uint32_t nq = __shfl_sync(FULL_MASK, hn, srcl);
-				const uint32_t h = quad_xxh32_prologue(sp, mine < 32 ? nq : 0u, lane);
-				// hand the digest to the owning lane: lane `mine` takes it from the first lane of quad q
-				uint32_t taken = 0;
-#pragma unroll
-				for (int qq = 0; qq < 8; qq++) {
-					const uint32_t owner = __shfl_sync(FULL_MASK, mine, qq * 4);
-					const uint32_t hv = __shfl_sync(FULL_MASK, h, qq * 4);
-					if (owner == static_cast<uint32_t>(lane)) computed = hv;
-					if (owner < 32) taken |= 1u << owner;
-				}
-				todo &= ~taken;
-			}
+			if (fresh) h_mode = H_NONE;
 			if (fresh && (hflags & LZ4B200_BLK_HAS_CHECKSUM) && state == L_RUN) {
 				const uint8_t *t = hs + hn;
 				declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
-				if (computed != declared) {
-					// :672-676 -- verified before any decoding
-					lz4b200_blk_status *st = status + blk;
-					st->code = LZ4B200_ST_BLOCK_CHECKSUM;
-					st->out_len = 0; st->err_pos = 0; st->aux = 0;
-					st->xxh32_computed = computed; st->xxh32_declared = declared;
-					state = L_IDLE;
-				}
+				h_mode = H_INLINE;
 			}
 			__syncwarp();
 		}
@@ -306,7 +306,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		}
 
 		// ================= parked work that needs the whole warp =================
-		uint32_t coop = __ballot_sync(FULL_MASK, state == L_GIANT || state == L_EXACT);
+		uint32_t coop = __ballot_sync(FULL_MASK, state == L_GIANT || state == L_EXACT || state == L_HASH);
 		if (coop) {
 			// (rare) the refills in flight must have landed before a lane restarts its in ring
 			cp_async_wait<0>();
@@ -325,9 +325,29 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				__syncwarp();
 				continue;
 			}
-			// one giant copy of lane j, straight in global memory (the lane has flushed its ring)
 			const uint8_t *sb = shfl_cptr(sbase, j);
+			if (stj == L_HASH) {
+				// the block's checksum over again (a giant made the lane skip parts of its in ring): quad 0 hashes,
+				// the lane compares and reports
+				const uint32_t begj = __shfl_sync(FULL_MASK, a_beg, j), endj = __shfl_sync(FULL_MASK, a_end, j);
+				const uint32_t h = __shfl_sync(FULL_MASK, quad_xxh32_prologue(sb + begj, lane < 4 ? endj - begj : 0u, lane), 0);
+				if (lane == j) {
+					lz4b200_blk_status *st = status + blk;
+					const bool okay = h == declared;
+					st->code = okay ? LZ4B200_ST_OK : LZ4B200_ST_BLOCK_CHECKSUM;
+					st->out_len = okay ? p_cur - p_start : 0u;
+					st->err_pos = 0;
+					st->aux = 0;
+					st->xxh32_computed = h;
+					st->xxh32_declared = declared;
+					state = L_IDLE;
+				}
+				__syncwarp();
+				continue;
+			}
+			// one giant copy of lane j, straight in global memory (the lane has flushed its ring)
 			uint8_t *ob = shfl_ptr(obase, j);
+			const uint32_t g_len = sq == S_LIT ? rem_lit : rem_ml, g_off = sq == S_LIT ? 0u : dist;
 			const uint32_t lenj = __shfl_sync(FULL_MASK, g_len, j), offj = __shfl_sync(FULL_MASK, g_off, j);
 			const uint32_t pj = __shfl_sync(FULL_MASK, p_cur, j), aj = __shfl_sync(FULL_MASK, a_cur, j);
 			__syncwarp();
@@ -389,7 +409,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 					rem_lit = lit;
 					sq = lit ? S_LIT : S_OFF;
 					progressed = true;
-					if (lit >= GIANT) { giant = true; g_len = lit; g_off = 0; }
+					if (lit >= GIANT) giant = true;
 				}
 			}
 		}
@@ -439,7 +459,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 						dist = off;
 						sq = S_MATCH;
 						progressed = true;
-						if (ml >= GIANT) { giant = true; g_len = ml; g_off = off; }
+						if (ml >= GIANT) giant = true;
 					}
 				}
 			}
@@ -496,6 +516,16 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		cp_async_wait<0>();
 		a_loaded += rf;
 		rf = 0;
+		// ================= fused block checksum: one stripe per trip, straight out of the in ring =================
+		{
+			const bool hs_ready = state == L_RUN && h_mode == H_INLINE && h_pos + 16u <= a_end && a_loaded >= h_pos + 16u;
+			if (__any_sync(FULL_MASK, hs_ready)) {
+				if (hs_ready) {
+					hash_stripe(inb, lane4, h_pos, acc0, acc1, acc2, acc3);
+					h_pos += 16;
+				}
+			}
+		}
 		// ================= stage 4: the match piece in flight, <= 32 bytes (Output_With_History, :845-904) =================
 		{
 			const uint32_t n = (state == L_EXACT) ? 0u : pend_n;
@@ -525,15 +555,31 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 					if (base16 + k >= p_start && base16 + k < p_cur) obase[base16 + k] = static_cast<uint8_t>(ws[k >> 2] >> (8 * (k & 3)));
 			}
 			if (state == L_FINISH) {
-				lz4b200_blk_status *st = status + blk;
-				st->code = LZ4B200_ST_OK;
-				st->out_len = p_cur - p_start;
-				st->err_pos = 0;
-				st->aux = 0;
-				st->xxh32_computed = computed;
-				st->xxh32_declared = declared;
-				state = L_IDLE;
+				uint32_t computed = 0;
+				bool okay = true;
+				if (h_mode == H_INLINE) {
+					// the stripes the hash is still behind (their chunks are kept in the in ring), then Final (:993-1017)
+					while (h_pos + 16u <= a_end) {
+						hash_stripe(inb, lane4, h_pos, acc0, acc1, acc2, acc3);
+						h_pos += 16;
+					}
+					computed = xxh_finish<true>(acc0, acc1, acc2, acc3, a_end - a_beg, sbase + h_pos, a_end - h_pos);
+					okay = computed == declared;
+				}
+				if (h_mode == H_REDO) {
+					state = L_HASH;   // needs a quad of the warp: next trip
+				} else {
+					lz4b200_blk_status *st = status + blk;
+					st->code = okay ? LZ4B200_ST_OK : LZ4B200_ST_BLOCK_CHECKSUM;   // :672-676, :702
+					st->out_len = okay ? p_cur - p_start : 0u;
+					st->err_pos = 0;
+					st->aux = 0;
+					st->xxh32_computed = computed;
+					st->xxh32_declared = declared;
+					state = L_IDLE;
+				}
 			} else {
+				if (h_mode == H_INLINE) h_mode = H_REDO;   // the giant's bytes never pass through the in ring
 				state = L_GIANT;
 			}
 			progressed = true;
@@ -569,7 +615,9 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			// (a length read from global memory may have carried a_cur past the loaded chunks: skip them)
 			if (a_loaded < (a_cur & ~15u)) a_loaded = a_cur & ~15u;
 			const uint32_t a_end16 = (a_end + 15u) & ~15u;
-			const bool room = state == L_RUN && a_loaded < a_end16 && a_loaded + 16u - (a_cur & ~15u) <= IN_BYTES;
+			// the oldest byte still needed: the decoder's position, or the checksum's if it is behind
+			const uint32_t a_tail = (h_mode == H_INLINE && h_pos < a_cur ? h_pos : a_cur) & ~15u;
+			const bool room = state == L_RUN && a_loaded < a_end16 && a_loaded + 16u - a_tail <= IN_BYTES;
 			if (room) {
 				const uint8_t *g = sbase + a_loaded;
 				const uint32_t u0 = ((a_loaded >> 2) << 7) | lane4;
