@@ -52,25 +52,34 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = auto")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--k1-group", type=int, default=0, help="blocks per warp in K1 (0 auto, -1 v1 kernel)")
+    ap.add_argument("--k1-group", type=int, default=0,
+                    help="K1 tuning (include/lz4b200.h): 0 auto, 50 v5, 40 v4, 64 v3, 1..16 v2, -1 v1")
     return ap.parse_args()
 
 
-def ncu_traffic(args):
+K1_PROFILE = "r01_s2_k1_ncu_full_4gib.csv"   # ncu --set full of the headline workload, summarised by tools/ncu_summary.py
+
+
+def ncu_traffic(args, kernel):
     """DRAM bytes (read + write) of one K1 launch from the committed `ncu --set full` capture of this
-    exact workload (profiles/r01_final_k1_ncu_full_4gib.csv); None for any other workload."""
+    exact workload and kernel (profiles/K1_PROFILE); None for any other workload or kernel."""
     if not (args.size_gib == 4.0 and args.kinds == "text" and args.block == "64k" and args.frame_mib == 1.0
             and not args.no_block_checksum):
         return None
     try:
         rd = wr = None
-        with open(os.path.join(ROOT, "profiles", "r01_final_k1_ncu_full_4gib.csv")) as f:
+        name = ""
+        with open(os.path.join(ROOT, "profiles", K1_PROFILE)) as f:
             for line in f:
                 parts = line.strip().split(",")
+                if parts[0] == "Kernel Name":
+                    name = parts[2]
                 if parts[0] == "dram__bytes_read.sum":
                     rd = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6}[parts[1]]
                 if parts[0] == "dram__bytes_write.sum":
                     wr = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6}[parts[1]]
+        if kernel not in name:
+            return None
         return int(rd + wr) if rd is not None and wr is not None else None
     except Exception:
         return None
@@ -326,6 +335,7 @@ def run_ours(args):
 
     traffic = batch.traffic()
     peak, peak_src = peaks()
+    k1_name = ctx.k1_kernel_name(batch.block_count)
     k1 = float(np.mean(k1_ms)) if k1_ms else 0.0
     k1_bytes = traffic["compressed_read"] + traffic["decompressed_written"]
     achieved = k1_bytes / (k1 / 1e3) / 1e9 if k1 > 0 else 0.0
@@ -342,8 +352,8 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
         "kernel_ms": {"k1_decode_blocks": k1, "k3_xxh32_frames": float(np.mean(k3_ms)) if k3_ms else 0.0},
-        "roofline": {"bound": "hbm", "kernel": "decode_blocks_v2_kernel (K1)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": k1_name + " (K1)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args, k1_name), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(k1_bytes),
                      "whole_step_frac": (k1_bytes + traffic["checksum_reread"]) / (ms_per_step / 1e3) / 1e9 / peak},
     }

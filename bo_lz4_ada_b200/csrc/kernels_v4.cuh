@@ -685,10 +685,17 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 			}
 			continue;
 		}
-		// a payload that can expand more than 32-fold is a handful of giant matches (zero pages, RLE): the exact
-		// routine's warp-wide length scan and pattern replication are the right tool, skip the parse machinery
+		// a block that opens with a match of 529 bytes or more (two 255 extension bytes: zero pages, RLE) is a
+		// handful of giant sequences: the exact routine's warp-wide length scan and pattern replication are the
+		// right tool, and the speculative parse would only chew on runs of 0xff
+		bool giant_first = false;
+		if (ng >= 8) {
+			const uint32_t tk = ld_u8<true>(sg);
+			const uint32_t l = tk >> 4;
+			if (l < 15 && (tk & 15u) == 15u && 4 + l < ng) giant_first = ld_u8<true>(sg + 3 + l) == 255u && ld_u8<true>(sg + 4 + l) == 255u;
+		}
 		uint32_t produced = 0;
-		const bool okay = !(ng < 131072u && capg >= 65536u && ng * 32u < capg) && decode_block(sg, ng, og, capg, wm, lane, produced);
+		const bool okay = !giant_first && decode_block(sg, ng, og, capg, wm, lane, produced);
 		__syncwarp();
 		if (static_cast<uint32_t>(lane) == g) {
 			if (okay) {
