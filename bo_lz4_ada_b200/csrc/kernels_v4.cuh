@@ -60,13 +60,19 @@ constexpr uint32_t STOP = 0xffffffffu;
 // of this token (Decompress_Sequence, lib/lz4ada.adb:737-777; lengths: Process_Variable_Length :724-735).
 __device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint32_t wlen, uint32_t last, uint32_t &st)
 {
+	// A length with more than GIANT_EXT extension bytes (a run of 256 KiB and more: zero pages, RLE) ends the fast
+	// path for the block (W_BAD): the exact routine scans such lengths 32 bytes at a time and replicates the
+	// pattern with vector stores, while the speculative chains here would crawl through the 0xff bytes one by one.
+	constexpr uint32_t GIANT_EXT = 1024;
 	const uint32_t tk = cw[p];
 	uint32_t lit = tk >> 4, q = p + 1;
 	const uint32_t stop_st = last ? W_BAD : W_CUT;
 	if (lit == 15) {
 		uint32_t b;
+		const uint32_t q0 = q;
 		do {
 			if (q >= wlen) { st = stop_st; return STOP; }
+			if (q - q0 > GIANT_EXT) { st = W_BAD; return STOP; }
 			b = cw[q++];
 			lit += b;
 		} while (b == 255);
@@ -82,8 +88,10 @@ __device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint3
 	uint32_t nx = e + 2;
 	if ((tk & 15) == 15) {
 		uint32_t b;
+		const uint32_t n0 = nx;
 		do {
 			if (nx >= wlen) { st = stop_st; return STOP; }
+			if (nx - n0 > GIANT_EXT) { st = W_BAD; return STOP; }
 			b = cw[nx++];
 		} while (b == 255);
 	}
@@ -691,8 +699,16 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 		bool giant_first = false;
 		if (ng >= 8) {
 			const uint32_t tk = ld_u8<true>(sg);
-			const uint32_t l = tk >> 4;
-			if (l < 15 && (tk & 15u) == 15u && 4 + l < ng) giant_first = ld_u8<true>(sg + 3 + l) == 255u && ld_u8<true>(sg + 4 + l) == 255u;
+			uint32_t l = tk >> 4, q = 1;
+			bool plain_len = true;
+			if (l == 15) {
+				const uint32_t e = ld_u8<true>(sg + 1);
+				l += e;
+				q = 2;
+				plain_len = e != 255u;
+			}
+			const uint32_t x = q + l + 2;   // first extension byte of the match length
+			if (plain_len && (tk & 15u) == 15u && x + 1 < ng) giant_first = ld_u8<true>(sg + x) == 255u && ld_u8<true>(sg + x + 1) == 255u;
 		}
 		uint32_t produced = 0;
 		const bool okay = !giant_first && decode_block(sg, ng, og, capg, wm, lane, produced);
