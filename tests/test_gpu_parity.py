@@ -593,6 +593,62 @@ def test_k1_v3_many_blocks_property(ctx):
         assert exc == "OK", (i, msg)
         assert out == data[(i % 13) * 1000:] + data[:(i % 13) * 1000], i
 
+
+@pytest.mark.parametrize("g", [50, 41])
+def test_k1_lane_refill_and_checksums_direct(ctx, oracle, g):
+    """300 blocks from 1 byte to 64 KiB (text, RLE, noise) with block checksums through lz4b200_decode_blocks:
+    v5 lanes finish at very different times and pull new blocks from the counter; every third block's checksum
+    trailer is corrupted and must come back as LZ4B200_ST_BLOCK_CHECKSUM with the right computed value."""
+    rng = np.random.default_rng(5)
+    text = corpus.text_like(400000, seed=77)
+    rle = corpus.rle_like(200000, seed=78)
+    blocks, expect, bad = [], [], []
+    for i in range(300):
+        n = int(rng.choice([1, 7, 64, 300, 2000, 9000, 30000, 65536]))
+        kind = i % 3
+        base = text if kind == 0 else rle if kind == 1 else bytes(rng.integers(0, 256, 70000, dtype=np.uint8))
+        o = int(rng.integers(0, len(base) - n))
+        plain = base[o:o + n]
+        blk = corpus.compress_block(plain)
+        h = corpus.xxh32(blk)
+        corrupt = i % 3 == 2 and i % 2 == 0
+        blocks.append(blk + struct.pack("<I", h ^ (0x10 if corrupt else 0)))
+        expect.append(plain)
+        bad.append(corrupt)
+    cap = 65536
+    stride = cap + 256
+    src = b"".join(blocks)
+    descs = (lz.BlkDesc * len(blocks))()
+    pos = 0
+    for i, blk in enumerate(blocks):
+        descs[i].src_off, descs[i].src_len = pos, len(blk) - 4
+        descs[i].dst_off, descs[i].dst_cap = i * stride + (i % 5), cap
+        descs[i].flags, descs[i].hist_avail = 2, 0   # LZ4B200_BLK_HAS_CHECKSUM
+        pos += len(blk)
+    d_src, d_dst = ctx.alloc(len(src)), ctx.alloc(stride * len(blocks))
+    d_desc, d_st = ctx.alloc(ctypes_sizeof(descs)), ctx.alloc(24 * len(blocks))
+    ctx.h2d(d_src, src)
+    ctx.h2d(d_desc, bytes(descs))
+    ctx.set_tuning(g)
+    try:
+        assert lz.lib().lz4b200_decode_blocks(ctx.handle, d_src, d_dst, len(blocks), d_desc, d_st) == 0
+    finally:
+        ctx.set_tuning(0)
+    st = ctx.d2h(d_st, 24 * len(blocks))
+    out = ctx.d2h(d_dst, stride * len(blocks))
+    for i, (blk, exp, corrupt) in enumerate(zip(blocks, expect, bad)):
+        code, out_len, _, _, computed, declared = struct.unpack_from("<IIIiII", st, 24 * i)
+        assert computed == corpus.xxh32(blk[:-4]), i
+        assert declared == struct.unpack("<I", blk[-4:])[0], i
+        if corrupt:
+            assert code == 1 and out_len == 0, (i, code)          # LZ4B200_ST_BLOCK_CHECKSUM
+        else:
+            assert code == 0 and out_len == len(exp), (i, code, out_len, len(exp))
+            o = descs[i].dst_off
+            assert out[o:o + out_len] == exp, i
+    for p in (d_src, d_dst, d_desc, d_st):
+        ctx.free(p)
+
 def test_py_decoder_agrees_on_vector(oracle):
     """Sanity of the test-side helper against a golden vector (keeps _py_decode honest)."""
     frame = _read("z100.lz4")
