@@ -446,8 +446,11 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 	// ---- matches, part 1: classify, and start the global loads of the old sources right away ----
 	const uint32_t src_s = mo - off;
 	const uint32_t src_e = src_s + (ml < off ? ml : off);   // self-overlap: the source ends where the match starts
-	const bool simple = ml <= 32 && off >= ml;
-	const bool is_far = ml != 0 && src_s < near_lo;          // then the whole source is in global memory
+	const bool is_far = ml != 0 && src_s < near_lo;          // then the whole source is in global memory ...
+	// ... except right behind a block's history (decode_block with hist > 0), where a source may begin in the
+	// history and end in bytes of this block that only the ring holds: the byte-wise cooperative copy sorts it out
+	const bool straddle = is_far && src_e > st.flushed;
+	const bool simple = ml <= 32 && off >= ml && !straddle;
 	Src48 S;
 	load_far(S, og, src_s, ml, is_far && simple);
 
@@ -560,11 +563,15 @@ __device__ __forceinline__ bool batch(WarpMem &wm, uint32_t phase, uint8_t *og, 
 }
 
 // One compressed block, start to finish, by one warp.  false = give it to the exact routine.
+// The block's output starts at og + hist; the hist bytes in front of it are final history of the same frame
+// that matches may reach into (0 for the independent blocks of K1; the stream window of the Update path).
+// Positions inside are relative to og, so an old source is simply a global read below the ring.
 __device__ __forceinline__ bool decode_block(const uint8_t *__restrict__ s, uint32_t n, uint8_t *og, uint32_t cap,
-					     WarpMem &wm, int lane, uint32_t &out_len)
+					     WarpMem &wm, int lane, uint32_t &out_len, uint32_t hist = 0)
 {
 	const uint32_t phase = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(og) & 15u);
-	BlockState st = {0, 0, 0};
+	BlockState st = {hist, hist, hist};
+	cap += hist;
 	uint32_t ip = 0;
 	while (ip < n) {
 		// ---------------- load the window ----------------
@@ -624,7 +631,7 @@ __device__ __forceinline__ bool decode_block(const uint8_t *__restrict__ s, uint
 		ip += wend;
 	}
 	flush_ring(wm.ring, phase, og, st.flushed, st.pos, lane);
-	out_len = st.pos;
+	out_len = st.pos - hist;
 	return true;
 }
 

@@ -540,12 +540,46 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 }
 
 // One block against a device-resident history window (single-block path under Update).
+// The K1 v4 block decoder (parallel parse, shared-memory ring) with the window in front of the cursor as
+// history; the exact routine takes over for anything unusual.
 __global__ void __launch_bounds__(32)
 stream_block_kernel(const uint8_t *__restrict__ src, uint8_t *win, const lz4b200_blk_desc *desc,
 		    lz4b200_blk_status *status)
 {
+	__shared__ v4::WarpMem wm;
 	const int lane = threadIdx.x & 31;
 	const lz4b200_blk_desc d = *desc;
+	if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_HASH_ONLY)) && d.dst_off < 0x70000000ull && d.dst_cap < 0x08000000u) {
+		uint32_t computed = 0, declared = 0;
+		bool sum_ok = true;
+		const uint8_t *s = src + d.src_off;
+		if (d.flags & LZ4B200_BLK_HAS_CHECKSUM) {   // verified before any decoding, lib/lz4ada.adb:672-676
+			const uint8_t *t = s + d.src_len;
+			declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+			computed = quad_xxh32_prologue(s, lane < 4 ? d.src_len : 0u, lane);
+			computed = __shfl_sync(FULL_MASK, computed, 0);
+			sum_ok = computed == declared;
+		}
+		if (sum_ok) {
+			// history the reference would accept: the frame's bytes in front of the cursor, at most what the
+			// window holds (hist_avail = 0xffffffff once its 64 KiB ring has wrapped)
+			const uint32_t before = static_cast<uint32_t>(d.dst_off);
+			const uint32_t hist = d.hist_avail < before ? d.hist_avail : before;
+			uint32_t produced = 0;
+			if (v4::decode_block(s, d.src_len, win + d.dst_off - hist, d.dst_cap, wm, lane, produced, hist)) {
+				if (lane == 0) {
+					status->code = LZ4B200_ST_OK;
+					status->out_len = produced;
+					status->err_pos = 0;
+					status->aux = 0;
+					status->xxh32_computed = computed;
+					status->xxh32_declared = declared;
+				}
+				return;
+			}
+		}
+		__syncwarp();
+	}
 	process_block<true>(src, win + d.dst_off, d, d.dst_cap, d.hist_avail, status, lane);
 }
 
