@@ -172,6 +172,7 @@ _SIGNATURES = {
                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32,
                                             ctypes.POINTER(BlkStatus)]),
     "lz4b200_stream_digest": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32)]),
+    "lz4b200_stream_adopt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]),
     # LZ4Ada API
     "lz4ada_set_device_context": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4ada_init": (ctypes.c_int, [c_int_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),

@@ -142,6 +142,10 @@ public:
 	int input_buffer_len;               // Input_Buffer'Length = In_Last + 1 (what the limit checks see)
 	std::vector<uint8_t> input_buffer;  // Input_Buffer(0 .. In_Last), grown on demand up to that length
 	BlockEngine *engine;
+	// While a block is handed to the engine straight out of the caller's Input (no copy): the rest of that
+	// Input behind the block -- what the caller will present again next time.  Null otherwise.
+	const uint8_t *lookahead = nullptr;
+	int lookahead_len = 0;
 	uint8_t *cache(size_t need);        // storage for the first `need` bytes of Input_Buffer
 
 private:

@@ -6,7 +6,17 @@
 // exception fires at the same byte.  What differs is where the work happens: a complete block
 // goes H2D, is decoded by one warp against a device-resident 64 KiB history window, and the
 // produced bytes come back D2H (lz4b200_stream_block).  There is no host-side LZ4 decoder.
+//
+// Read-ahead: when a block arrives straight out of a large Input and the
+// independent blocks behind it are complete in that Input too, they are all decoded by ONE K1
+// launch into a staging buffer; the following Update calls then only check that the caller presents
+// the same bytes again, copy their block out of the staging buffer and let the stream adopt it
+// (history window + running content checksum).  Every call still reports exactly one block, the same
+// Num_Consumed / Output_First / Output_Last as the reference, and an erroneous block is never
+// cached: it goes through the one-block path when its turn comes, with the same exception.
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.hpp"
 
@@ -40,12 +50,20 @@ public:
 	explicit DeviceStreamEngine(int stream_block_max) : max_block_(uint32_t(stream_block_max)) {}
 	~DeviceStreamEngine() override
 	{
+		if (ctx_) {
+			if (d_src_) lz4b200_free(ctx_, d_src_);
+			if (d_stage_) lz4b200_free(ctx_, d_stage_);
+			if (d_desc_) lz4b200_free(ctx_, d_desc_);
+			if (d_stat_) lz4b200_free(ctx_, d_stat_);
+			if (h_stage_) lz4b200_free_host(ctx_, h_stage_);
+		}
 		if (stream_) lz4b200_stream_destroy(stream_);
 	}
 
 	Raised new_frame(Walker &) override   // Reset_Outer_For_Next_Frame, lib/lz4ada.adb:451-461
 	{
 		output_pos_ = 0;
+		drop_ahead();
 		if (stream_ && lz4b200_stream_reset(stream_) != LZ4B200_OK) return device_failure();
 		return ok();
 	}
@@ -64,7 +82,31 @@ public:
 		if (w.m.block_checksum_length) flags |= LZ4B200_BLK_HAS_CHECKSUM;
 		lz4b200_blk_status st;
 		memset(&st, 0, sizeof st);
-		if (lz4b200_stream_block(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
+		// ---- read-ahead: served from the staging buffer, or decoded together with the blocks behind it ----
+		bool served = false;
+		if (ahead_pos_ < ahead_.size()) {
+			const Ahead &e = ahead_[ahead_pos_];
+			if (e.blk_len == blk_len && e.flags == flags && memcmp(blk, ahead_copy_.data() + e.copy_off, size_t(blk_len)) == 0)
+				served = true;
+			else
+				drop_ahead();   // the caller came back with something else
+		}
+		if (!served && ahead_pos_ >= ahead_.size() && w.lookahead && read_ahead(w, blk, blk_len, flags)) served = true;
+		if (served) {
+			const Ahead &e = ahead_[ahead_pos_];
+			if (int64_t(e.st.out_len) <= cap) {
+				st = e.st;
+				if (st.out_len) memcpy(buffer + output_pos_, h_stage_ + e.out_off, st.out_len);
+				if (lz4b200_stream_adopt(stream_, d_stage_ + e.out_off, st.out_len, w.m.content_checksum_length != 0) != LZ4B200_OK)
+					return device_failure();
+				ahead_pos_++;
+			} else {
+				served = false;   // does not fit the caller's Buffer here: the one-block path reports it
+				drop_ahead();
+			}
+		}
+		if (!served &&
+		    lz4b200_stream_block(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
 					 buffer + output_pos_, uint32_t(cap), &st) != LZ4B200_OK)
 			return device_failure();
 		// Decrease_Data_Size_Remaining (:826-839) fires inside Write_Output, i.e. before any
@@ -97,6 +139,123 @@ public:
 	}
 
 private:
+	// ---- read-ahead -----------------------------------------------------------------------
+	struct Ahead {
+		size_t copy_off;          // payload (+ trailer) of the block in ahead_copy_
+		int blk_len;
+		uint32_t flags;
+		uint32_t out_off;         // its decoded bytes in the staging buffers
+		lz4b200_blk_status st;    // always LZ4B200_ST_OK
+	};
+	static constexpr int kAheadMaxBlocks = 64;
+	static constexpr uint64_t kAheadMaxBytes = 32ull << 20;   // decoded bytes per read-ahead
+
+	void drop_ahead()
+	{
+		ahead_.clear();
+		ahead_pos_ = 0;
+	}
+
+	// Decode `blk` and the complete independent blocks behind it in the caller's Input with one K1 launch.
+	// true = the cache now starts with `blk` (decoded fine); false = nothing cached, use the one-block path.
+	bool read_ahead(Walker &w, const uint8_t *blk, int blk_len, uint32_t flags)
+	{
+		drop_ahead();
+		if (w.m.format != Format::Modern || !w.m.block_independent || w.lookahead != blk + blk_len) return false;
+		const int bc = w.m.block_checksum_length;
+		const uint32_t block_max = uint32_t(w.m.frame_block_max);
+		if (block_max == 0 || block_max > max_block_) return false;
+		const uint32_t stride = (block_max + 255u) & ~255u;
+		struct Item { size_t off; int len; uint32_t flags; };
+		std::vector<Item> items;
+		items.push_back({0, blk_len, flags});
+		const uint8_t *p = w.lookahead, *end = w.lookahead + w.lookahead_len;
+		while (int(items.size()) < kAheadMaxBlocks && uint64_t(items.size() + 1) * stride <= kAheadMaxBytes) {
+			// the size word as Try_Detect_Input_Length reads it (lib/lz4ada.adb:525-585)
+			if (end - p < kBlockSizeBytes) break;
+			uint32_t word = load32(p);
+			if (word == 0) break;   // end mark
+			const bool stored = (word & 0x80000000u) != 0;
+			word &= 0x7ffffffu;
+			if (int64_t(word) + kBlockSizeBytes + bc > int64_t(w.input_buffer_len)) break;   // the walker raises this one
+			const int total = int(word) + bc;
+			if (end - (p + kBlockSizeBytes) < total) break;   // not complete in this Input
+			uint32_t f = stored ? LZ4B200_BLK_STORED : 0u;
+			if (bc) f |= LZ4B200_BLK_HAS_CHECKSUM;
+			items.push_back({size_t(p + kBlockSizeBytes - blk), total, f});
+			p += kBlockSizeBytes + total;
+		}
+		if (items.size() < 2) return false;
+		const size_t n = items.size();
+		const size_t span = items.back().off + size_t(items.back().len);
+		if (!reserve(span + 64, n * size_t(stride) + 64, n)) return false;
+		std::vector<lz4b200_blk_desc> descs(n);
+		for (size_t i = 0; i < n; i++) {
+			descs[i].src_off = items[i].off;
+			descs[i].src_len = uint32_t(items[i].len - bc);
+			descs[i].dst_off = uint64_t(i) * stride;
+			descs[i].dst_cap = block_max;
+			descs[i].flags = items[i].flags;
+			descs[i].hist_avail = 0;
+		}
+		std::vector<lz4b200_blk_status> stats(n);
+		if (lz4b200_h2d(ctx_, d_src_, blk, span) != LZ4B200_OK ||
+		    lz4b200_h2d(ctx_, d_desc_, descs.data(), sizeof(lz4b200_blk_desc) * n) != LZ4B200_OK ||
+		    lz4b200_decode_blocks(ctx_, d_src_, d_stage_, uint32_t(n), d_desc_, d_stat_) != LZ4B200_OK ||
+		    lz4b200_d2h(ctx_, stats.data(), d_stat_, sizeof(lz4b200_blk_status) * n) != LZ4B200_OK ||
+		    lz4b200_d2h(ctx_, h_stage_, d_stage_, n * size_t(stride)) != LZ4B200_OK || lz4b200_sync(ctx_) != LZ4B200_OK)
+			return false;
+		// keep the leading run of good blocks; the first one that is not (an error, or a block that reaches into
+		// its predecessor) and everything behind it take the one-block path when their turn comes
+		size_t good = 0;
+		while (good < n && stats[good].code == LZ4B200_ST_OK) good++;
+		if (good == 0) return false;
+		ahead_copy_.assign(blk, blk + items[good - 1].off + size_t(items[good - 1].len));
+		for (size_t i = 0; i < good; i++) ahead_.push_back({items[i].off, items[i].len, items[i].flags, uint32_t(i) * stride, stats[i]});
+		return true;
+	}
+
+	bool reserve(size_t src_bytes, size_t stage_bytes, size_t n)
+	{
+		if (src_bytes > cap_src_) {
+			if (d_src_) lz4b200_free(ctx_, d_src_);
+			d_src_ = nullptr;
+			cap_src_ = 0;
+			if (lz4b200_alloc(ctx_, src_bytes, reinterpret_cast<void **>(&d_src_)) != LZ4B200_OK) return false;
+			cap_src_ = src_bytes;
+		}
+		if (stage_bytes > cap_stage_) {
+			if (d_stage_) lz4b200_free(ctx_, d_stage_);
+			if (h_stage_) lz4b200_free_host(ctx_, h_stage_);
+			d_stage_ = h_stage_ = nullptr;
+			cap_stage_ = 0;
+			if (lz4b200_alloc(ctx_, stage_bytes, reinterpret_cast<void **>(&d_stage_)) != LZ4B200_OK ||
+			    lz4b200_alloc_host(ctx_, stage_bytes, reinterpret_cast<void **>(&h_stage_)) != LZ4B200_OK)
+				return false;
+			cap_stage_ = stage_bytes;
+		}
+		if (n > cap_n_) {
+			if (d_desc_) lz4b200_free(ctx_, d_desc_);
+			if (d_stat_) lz4b200_free(ctx_, d_stat_);
+			d_desc_ = nullptr;
+			d_stat_ = nullptr;
+			cap_n_ = 0;
+			if (lz4b200_alloc(ctx_, sizeof(lz4b200_blk_desc) * n, reinterpret_cast<void **>(&d_desc_)) != LZ4B200_OK ||
+			    lz4b200_alloc(ctx_, sizeof(lz4b200_blk_status) * n, reinterpret_cast<void **>(&d_stat_)) != LZ4B200_OK)
+				return false;
+			cap_n_ = n;
+		}
+		return true;
+	}
+
+	std::vector<Ahead> ahead_;
+	size_t ahead_pos_ = 0;
+	std::vector<uint8_t> ahead_copy_;
+	uint8_t *d_src_ = nullptr, *d_stage_ = nullptr, *h_stage_ = nullptr;
+	lz4b200_blk_desc *d_desc_ = nullptr;
+	lz4b200_blk_status *d_stat_ = nullptr;
+	size_t cap_src_ = 0, cap_stage_ = 0, cap_n_ = 0;
+
 	Raised ensure_stream()
 	{
 		if (stream_) return ok();

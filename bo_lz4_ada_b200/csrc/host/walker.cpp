@@ -285,7 +285,12 @@ Raised Walker::handle_newly_known_input_length(const uint8_t *input, int input_l
 		block_end_consumed = consumed;
 		m.input_buffer_filled = 0;
 		input_length = -1;
-		return engine->block(*this, blk, total, buffer, buffer_len, of, ol);
+		lookahead = input + consumed;
+		lookahead_len = input_len - consumed;
+		const Raised r = engine->block(*this, blk, total, buffer, buffer_len, of, ol);
+		lookahead = nullptr;
+		lookahead_len = 0;
+		return r;
 	}
 	return cache_data_and_process_if_full(input, input_len, consumed, buffer, buffer_len, of, ol);
 }

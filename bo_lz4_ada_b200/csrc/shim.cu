@@ -1291,6 +1291,30 @@ int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t sr
 	return LZ4B200_OK;
 }
 
+int lz4b200_stream_adopt(lz4b200_stream *s, const uint8_t *dev_bytes, uint32_t n, int hash_content)
+{
+	if (!s || (!dev_bytes && n)) return LZ4B200_ERR_ARG;
+	lz4b200_ctx *ctx = s->ctx;
+	if (n > s->max_block) return LZ4B200_ERR_ARG;
+	if (n == 0) return LZ4B200_OK;
+	// keep the last 64 KiB in front of the cursor; compact when the window is exhausted
+	if (s->cursor + n > s->win_size) {
+		CK(cudaMemcpyAsync(s->d_win, s->d_win + s->cursor - HISTORY, HISTORY, cudaMemcpyDeviceToDevice,
+				   ctx->stream));
+		s->cursor = HISTORY;
+	}
+	CK(cudaMemcpyAsync(s->d_win + s->cursor, dev_bytes, n, cudaMemcpyDeviceToDevice, ctx->stream));
+	if (hash_content) {
+		xxh32_stream_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH),
+							       s->d_win + s->cursor, n, nullptr);
+		ctx->launches++;
+		CK(cudaGetLastError());
+	}
+	s->cursor += n;
+	s->frame_pos += n;
+	return LZ4B200_OK;
+}
+
 int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32)
 {
 	if (!s || !xxh32) return LZ4B200_ERR_ARG;

@@ -235,6 +235,12 @@ int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t sr
 		lz4b200_blk_status *status);
 /* XXH32 of every byte produced since the last reset (XXHash32.Final, :993-1017). */
 int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32);
+/* Read-ahead support: n decoded bytes that already sit in device memory
+ * (a block decoded ahead of time by lz4b200_decode_blocks into a staging buffer) become the next
+ * bytes of the stream -- appended to its history window and, if hash_content, folded into its
+ * running content checksum, exactly what lz4b200_stream_block does for a block it decodes itself.
+ * Asynchronous on the context's current stream. */
+int lz4b200_stream_adopt(lz4b200_stream *s, const uint8_t *dev_bytes, uint32_t n, int hash_content);
 
 /* ------------------------------------------------------------------------
  * LZ4Ada package API  (reference lib/lz4ada.ads)

@@ -98,6 +98,91 @@ def test_update_step_parity_with_oracle(ctx, oracle):
                 pos += ra[0]
 
 
+
+def _step_parity(lz_dec, o_dec, data, chunk):
+    """Feed both decompressors the same pieces; every call must agree on Num_Consumed, the bytes,
+    Output_First/Last and Is_End_Of_Frame, and on the exception that ends the run (if any)."""
+    pos = 0
+    while pos < len(data):
+        piece = data[pos:pos + chunk]
+        ea = eb = None
+        try:
+            ra = lz_dec.Update(piece)
+        except lz.LZ4AdaError as e:
+            ea = (e.ada_name, e.information)
+        try:
+            rb = o_dec.update(piece)
+        except Exception as e:   # OracleError
+            eb = (e.name, "raised LZ4ADA.%s : %s" % (e.name, e) if False else None)
+            eb = (e.name, None)
+        if ea or eb:
+            assert ea is not None and eb is not None and ea[0] == eb[0], (pos, ea, eb)
+            return ea
+        assert ra == rb, (chunk, pos, ra[0], rb[0], ra[2:], rb[2:], len(ra[1]), len(rb[1]))
+        assert lz_dec.Is_End_Of_Frame() == o_dec.is_end_of_frame()
+        assert ra[0] > 0 or ra[1], "no progress"
+        pos += ra[0]
+    return None
+
+
+def test_update_read_ahead_step_parity(ctx, oracle):
+    """Large Inputs trigger the read-ahead (many blocks decoded by one K1 launch, handed out one per Update
+    call): per-call parity with the oracle must be exactly what it is for small Inputs -- good vectors, synthetic
+    frames of every block size with and without block checksums / content size, concatenations, and corrupted
+    streams (the exception must fire in the same call)."""
+    cases = []
+    for stem in ["t300k", "t301k", "t1111k", "b3444k", "concat390", "z101legacyplus", "skipz100", "z2841", "concatlegacy", "z9m"]:
+        cases.append((stem, _read(stem + ".lz4")))
+    text = corpus.text_like(900000, seed=21)
+    rle = corpus.rle_like(300000, seed=22)
+    rnd = corpus.random_bytes(150000, seed=23)
+    mix = text[:400000] + rnd + rle + text[400000:]
+    for code in (4, 5, 6, 7):
+        for bchk in (False, True):
+            cases.append(("mix-b%d-%d" % (code, bchk), corpus.build_frame(mix, code, bchk, True, True)))
+    cases.append(("mix-linked", corpus.build_frame(mix, 4, True, True, True, independent=False)))
+    cases.append(("short-interior", corpus.build_frame(text[:300000], 4, True, True, block_size=50000)))
+    cases.append(("two-frames", corpus.build_frame(text[:200000], 4, True, True) + corpus.build_frame(rle[:99999], 5, False, True, True)))
+    rng = np.random.default_rng(31)
+    base = corpus.build_frame(mix[:500000], 4, True, True, True)
+    for k, bad in enumerate(_mutations(base, rng, 24)):
+        cases.append(("mutation-%d" % k, bad))
+    ends = {}
+    for name, data in cases:
+        for chunk in (len(data), 1 << 20, 200000 + 7):
+            e = _step_parity(lz.Init(), oracle.init(), data, chunk)
+            ends.setdefault(name, e)
+            assert ends[name] == e or (ends[name] and e and ends[name][0] == e[0]), (name, chunk, ends[name], e)
+    assert any(v for k, v in ends.items() if k.startswith("mutation")), "no mutation raised"
+
+
+def test_update_read_ahead_changed_input(ctx):
+    """The caller does not have to present the same bytes again: if what follows differs from what was decoded
+    ahead, the staged blocks are dropped and the new bytes are decoded."""
+    a = corpus.text_like(400000, seed=41)
+    b = corpus.text_like(400000, seed=42)
+    fa, fb = corpus.build_frame(a, 4, False, False), corpus.build_frame(b, 4, False, False)
+    # same 7-byte header, different blocks: take the first block of `fa` out of the whole of `fa` (the blocks behind
+    # it are decoded ahead), then continue with the second block of `fb`
+    assert fa[:7] == fb[:7]
+    dec = lz.Init()
+    pos, o1 = 0, b""
+    while not o1:
+        c, o1, _, _ = dec.Update(fa[pos:])
+        pos += c
+    assert o1 == a[:65536]
+    n1a = struct.unpack_from("<I", fa, 7)[0] & 0x7fffffff
+    n1b = struct.unpack_from("<I", fb, 7)[0] & 0x7fffffff
+    assert pos == 7 + 4 + n1a
+    pos_b = 7 + 4 + n1b
+    out = bytearray(o1)
+    while pos_b < len(fb):
+        c, o, _, _ = dec.Update(fb[pos_b:])
+        assert c > 0 or o
+        out += o
+        pos_b += c
+    assert bytes(out) == a[:65536] + b[65536:]
+
 @pytest.mark.parametrize("stem", ERR)
 def test_error_case(ctx, stem):
     """Test_Error_Case (lz4test.adb:280-351): first 10 001 bytes, Init_With_Header(Single_Frame);
