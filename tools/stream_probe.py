@@ -20,20 +20,28 @@ def main():
     frame = corpus.build_frame(plain, code, True, True, False, not linked)
     ctx = lz.DeviceContext(0)
     ctx.make_default()
-    for rep in range(2):
-        dec = lz.Init()
-        out = bytearray()
-        pos = 0
-        t0 = time.perf_counter()
-        while pos < len(frame):
-            c, o, _, _ = dec.Update(frame[pos:pos + (1 << 20)])
-            out += o
-            pos += c
-        dt = time.perf_counter() - t0
-        assert bytes(out) == plain
-        print("Update loop: %d MiB, block code %d, %s: %.1f ms -> %.1f MB/s decompressed" % (
-            mib, code, "linked" if linked else "independent", 1e3 * dt, len(plain) / dt / 1e6), flush=True)
-        dec.close()
+    import numpy as np
+    arr = np.frombuffer(bytearray(frame), dtype=np.uint8)   # writable: slices reach the library without a copy
+    for feed in (1 << 16, 1 << 20, 8 << 20, len(frame)):
+        best = None
+        for rep in range(2):
+            dec = lz.Init()
+            total = 0
+            pos = 0
+            t0 = time.perf_counter()
+            first = b""
+            while pos < len(frame):
+                c, o, _, _ = dec.Update(arr[pos:pos + feed])
+                if not first:
+                    first = o
+                total += len(o)
+                pos += c
+            dt = time.perf_counter() - t0
+            assert total == len(plain) and first == plain[:len(first)]
+            best = dt if best is None or dt < best else best
+            dec.close()
+        print("Update loop: %d MiB, block code %d, %s, Input pieces of %d KiB: %.1f ms -> %.1f MB/s decompressed" % (
+            mib, code, "linked" if linked else "independent", feed >> 10, 1e3 * best, len(plain) / best / 1e6), flush=True)
     lz.lib().lz4ada_set_device_context(None)
     ctx.close()
 
