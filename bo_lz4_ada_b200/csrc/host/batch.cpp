@@ -16,6 +16,7 @@
 // the last block of a frame that is followed by another frame of the same stream is sized first
 // by K5.  A stream that violates the assumption (short interior block, match into the previous
 // block of an "independent" frame) is decoded again as one chain with exact running placement.
+#include <thread>
 #include <cstdlib>
 #include <algorithm>
 #include <memory>
@@ -430,46 +431,81 @@ int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_by
 	b->reservation = reservation;
 	b->src_bytes = src_bytes;
 	b->items.resize(n_items);
-	PlanEngine engine;
-	engine.frames = &b->frames;
-	engine.descs = &b->descs;
 	const int in_last = block_size_of(reservation) + 4 + kBlockSizeBytes - 1;   // as Init, lib/lz4ada.adb:60
-	for (uint32_t k = 0; k < n_items; k++) {
-		ItemPlan &it = b->items[k];
-		it.src_off = items[k].src_off;
-		it.src_len = items[k].src_len;
-		it.dst_off = items[k].dst_off;
-		it.dst_cap = items[k].dst_cap;
-		it.user_placed = items[k].dst_cap != 0;
-		it.first_frame = uint32_t(b->frames.size());
-		it.first_block = uint32_t(b->descs.size());
-		if (it.src_off > src_bytes || it.src_len > src_bytes - it.src_off) return LZ4ADA_ASSERTION_ERROR;
-		Meta m;
-		m.reservation = reservation;
-		Walker w(m, in_last, &engine);
-		engine.item = &it;
-		engine.cur = -1;
-		const uint8_t *s = src_host + it.src_off;
-		uint64_t pos = 0;
-		int idle = 0;
-		while (pos < it.src_len) {
-			const uint64_t left = it.src_len - pos;
-			const int window = int(std::min<uint64_t>(left, 0x40000000ull));
-			int consumed = 0, of = 1, ol = 0;
-			engine.call_pos = pos;
-			Raised r = w.update(s + pos, window, consumed, nullptr, 0, of, ol);
-			if (r) {
-				it.host_error = r;
-				break;
+	for (uint32_t k = 0; k < n_items; k++)
+		if (items[k].src_off > src_bytes || items[k].src_len > src_bytes - items[k].src_off) return LZ4ADA_ASSERTION_ERROR;
+	// Streams are independent: walk them on a few host threads (the walk touches one size word per block, spread
+	// over the whole compressed buffer -- 10 ms for 4096 frames / 65536 blocks on one thread), each thread into its
+	// own frame / block tables, which are then appended in stream order.
+	struct Part {
+		std::vector<FramePlan> frames;
+		std::vector<lz4b200_blk_desc> descs;
+	};
+	const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+	const uint32_t n_parts = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(8u, hw), n_items / 64u));
+	std::vector<Part> parts(n_parts);
+	auto walk_range = [&](uint32_t part) {
+		Part &pt = parts[part];
+		PlanEngine engine;
+		engine.frames = &pt.frames;
+		engine.descs = &pt.descs;
+		const uint32_t k0 = uint32_t(uint64_t(n_items) * part / n_parts), k1 = uint32_t(uint64_t(n_items) * (part + 1) / n_parts);
+		for (uint32_t k = k0; k < k1; k++) {
+			ItemPlan &it = b->items[k];
+			it.src_off = items[k].src_off;
+			it.src_len = items[k].src_len;
+			it.dst_off = items[k].dst_off;
+			it.dst_cap = items[k].dst_cap;
+			it.user_placed = items[k].dst_cap != 0;
+			it.first_frame = uint32_t(pt.frames.size());   // part-relative until the tables are joined
+			it.first_block = uint32_t(pt.descs.size());
+			Meta m;
+			m.reservation = reservation;
+			Walker w(m, in_last, &engine);
+			engine.item = &it;
+			engine.cur = -1;
+			const uint8_t *s = src_host + it.src_off;
+			uint64_t pos = 0;
+			int idle = 0;
+			while (pos < it.src_len) {
+				const uint64_t left = it.src_len - pos;
+				const int window = int(std::min<uint64_t>(left, 0x40000000ull));
+				int consumed = 0, of = 1, ol = 0;
+				engine.call_pos = pos;
+				Raised r = w.update(s + pos, window, consumed, nullptr, 0, of, ol);
+				if (r) {
+					it.host_error = r;
+					break;
+				}
+				pos += uint64_t(consumed);
+				if (consumed == 0 && ++idle > 2) {
+					it.host_error = err_assertion("No more data accepted but no exception signalled.");
+					break;
+				}
+				if (consumed) idle = 0;
 			}
-			pos += uint64_t(consumed);
-			if (consumed == 0 && ++idle > 2) {
-				it.host_error = err_assertion("No more data accepted but no exception signalled.");
-				break;
-			}
-			if (consumed) idle = 0;
+			it.eof = w.is_end_of_frame();
 		}
-		it.eof = w.is_end_of_frame();
+	};
+	if (n_parts == 1) {
+		walk_range(0);
+	} else {
+		std::vector<std::thread> workers;
+		for (uint32_t p = 1; p < n_parts; p++) workers.emplace_back(walk_range, p);
+		walk_range(0);
+		for (std::thread &t : workers) t.join();
+	}
+	for (uint32_t part = 0; part < n_parts; part++) {
+		Part &pt = parts[part];
+		const uint32_t f0 = uint32_t(b->frames.size()), d0 = uint32_t(b->descs.size());
+		const uint32_t k0 = uint32_t(uint64_t(n_items) * part / n_parts), k1 = uint32_t(uint64_t(n_items) * (part + 1) / n_parts);
+		for (uint32_t k = k0; k < k1; k++) {
+			b->items[k].first_frame += f0;
+			b->items[k].first_block += d0;
+		}
+		for (FramePlan &fp : pt.frames) fp.first_block += d0;
+		b->frames.insert(b->frames.end(), pt.frames.begin(), pt.frames.end());
+		b->descs.insert(b->descs.end(), pt.descs.begin(), pt.descs.end());
 	}
 	// blocks whose size decides where the next frame of the same stream starts
 	for (ItemPlan &it : b->items)
