@@ -203,6 +203,8 @@ _SIGNATURES = {
     "lz4ada_batch_traffic": (None, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
                                     ctypes.POINTER(ctypes.c_uint64)]),
     "lz4ada_batch_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "lz4ada_batch_exact_sizing": (ctypes.c_int, [ctypes.c_void_p]),
+    "lz4ada_batch_retried_streams": (ctypes.c_uint32, [ctypes.c_void_p]),
     "lz4ada_batch_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run_pipelined": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -517,6 +519,14 @@ class Batch:
                         "message": lib().lz4ada_batch_message(self._h, k).decode()})
         return out
 
+    def exact_sizing(self):
+        """Size every block with K5 at upload time and place the blocks back to back (before upload())."""
+        if lib().lz4ada_batch_exact_sizing(self._h) != 0:
+            raise Assertion_Error("raised LZ4ADA.ASSERTION_ERROR : exact_sizing after upload")
+
+    def retried_streams(self):
+        return lib().lz4ada_batch_retried_streams(self._h)
+
     def kernel_ms(self):
         """Device time of K1 / K4 / K3 in the last run (CUDA events on the launching stream)."""
         ms = (ctypes.c_float * 3)()
@@ -540,20 +550,27 @@ class Batch:
             pass
 
 
-def batch_decompress(ctx, streams, Reservation="For_All"):
-    """Convenience over Batch for host data: list of bytes -> list of (exception, output, eof, message)."""
+def batch_decompress(ctx, streams, Reservation="For_All", exact_sizing=False, info=None):
+    """Convenience over Batch for host data: list of bytes -> list of (exception, output, eof, message).
+    exact_sizing: size every block first (K5) and place the blocks back to back.  info: optional dict that
+    receives {"output_bytes", "retried_streams"} of the run."""
     offs, pos = [], 0
     for s in streams:
         offs.append((pos, len(s)))
         pos += len(s)
     src = b"".join(bytes(s) for s in streams) or b"\0"
     b = Batch(ctx, src, offs, Reservation)
+    if exact_sizing:
+        b.exact_sizing()
     need = b.output_bytes
     d_src = ctx.alloc(len(src) + 64)
     d_dst = ctx.alloc(need + 64)
     try:
         b.upload(d_src)
         b.run(d_src, d_dst)
+        if info is not None:
+            info["output_bytes"] = b.output_bytes
+            info["retried_streams"] = b.retried_streams()
         out = []
         for r in b.results():
             data = ctx.d2h(d_dst + r["dst_off"], r["out_len"]) if r["out_len"] else b""

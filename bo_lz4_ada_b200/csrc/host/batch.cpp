@@ -132,6 +132,7 @@ struct lz4ada_batch {
 	std::vector<lz4b200_blk_desc> descs;
 	std::vector<lz4b200_chain> chains;
 	std::vector<lz4b200_frame_blocks> hash_frames;   // frames whose content checksum K3 computes
+	bool exact_sizing = false;                       // lz4ada_batch_exact_sizing: K5 sizes every block first
 	std::vector<uint32_t> presize;                   // blocks K5 sizes before placement
 	std::vector<uint32_t> sized;                     // their sizes once K5 has run
 	bool have_sized = false;
@@ -177,7 +178,8 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 {
 	std::vector<int64_t> known(b->descs.size(), -1);
 	if (sized_len)
-		for (size_t i = 0; i < b->presize.size(); i++) known[b->presize[i]] = (*sized_len)[i];
+		for (size_t i = 0; i < b->presize.size(); i++)
+			if ((*sized_len)[i] != 0xffffffffu) known[b->presize[i]] = (*sized_len)[i];   // 0xffffffff: K5 gave up on it
 	b->chains.clear();
 	b->hash_frames.clear();
 	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of
@@ -209,13 +211,23 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			// a big block is ~10^5 sequences in series: give it the pipelined chain kernel (one CTA)
 			fp.solo = solo_on && !fp.chained && fp.block_max >= (1u << 20);
 			fp.hash_slot = 0xffffffffu;
+			// blocks sit one block-maximum apart (the frame format has no per-block decompressed size) -- unless K5
+			// has sized every block in front of this one (exact-sizing mode): then they sit back to back
+			uint64_t run = 0;
+			bool run_known = true;
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
-				d.dst_off = fp.dst_off + uint64_t(i) * fp.block_max;
+				const uint64_t off_i = run_known && !fp.chained ? run : uint64_t(i) * fp.block_max;
+				d.dst_off = fp.dst_off + off_i;
 				const uint64_t room = d.dst_off < item_end ? item_end - d.dst_off : 0;
-				d.dst_cap = uint32_t(std::min<uint64_t>(fp.block_max, room));
-				if (room < fp.block_max && i + 1 < fp.n_blocks) it.slow = true;   // tight user buffer
-				const uint64_t hist = uint64_t(i) * fp.block_max;
+				const int64_t ki = known[fp.first_block + i];
+				const bool exact_i = run_known && !fp.chained && ki >= 0;
+				d.dst_cap = uint32_t(std::min<uint64_t>(exact_i ? uint64_t(ki) : fp.block_max, room));
+				if (!exact_i && room < fp.block_max && i + 1 < fp.n_blocks) it.slow = true;   // tight user buffer
+				if (exact_i && room < uint64_t(ki)) it.slow = true;
+				if (ki >= 0) run += uint64_t(ki);
+				else run_known = false;
+				const uint64_t hist = off_i;
 				d.hist_avail = hist > 0xfffffffeull ? 0xffffffffu : uint32_t(hist);
 				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
 				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
@@ -252,7 +264,8 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			if (fp.n_blocks) {
 				const uint32_t last = fp.first_block + fp.n_blocks - 1;
 				const int64_t k = known[last];
-				fsize = uint64_t(fp.n_blocks - 1) * fp.block_max + (k >= 0 ? uint64_t(k) : fp.block_max);
+				if (run_known && !fp.chained) fsize = run;   // every block sized: the frame is exactly this long
+				else fsize = uint64_t(fp.n_blocks - 1) * fp.block_max + (k >= 0 ? uint64_t(k) : fp.block_max);
 			}
 			pos += fsize;
 		}
@@ -558,6 +571,34 @@ void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read, uint
 	if (checksum_reread) *checksum_reread = b ? b->t_reread : 0;
 }
 
+int lz4ada_batch_exact_sizing(lz4ada_batch *b)
+{
+	if (!b || b->tables_uploaded) return LZ4ADA_ASSERTION_ERROR;
+	b->exact_sizing = true;
+	b->presize.clear();
+	for (const FramePlan &fp : b->frames) {
+		if (!(fp.independent || fp.n_blocks <= 1)) continue;   // linked frames are chains: placed exactly as they run
+		for (uint32_t i = 0; i < fp.n_blocks; i++) b->presize.push_back(fp.first_block + i);
+	}
+	// the last block of a linked frame that is followed by another frame still decides that frame's base
+	for (const ItemPlan &it : b->items)
+		for (uint32_t f = 0; f + 1 < it.n_frames; f++) {
+			const FramePlan &fp = b->frames[it.first_frame + f];
+			if (!(fp.independent || fp.n_blocks <= 1) && fp.n_blocks) b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+		}
+	if (!b->presize.empty()) b->placed = false;
+	return LZ4ADA_OK;
+}
+
+uint32_t lz4ada_batch_retried_streams(const lz4ada_batch *b)
+{
+	uint32_t n = 0;
+	if (b)
+		for (const ItemPlan &it : b->items)
+			if (it.slow) n++;
+	return n;
+}
+
 int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3])
 {
 	if (!b || !ms) return LZ4ADA_ASSERTION_ERROR;
@@ -607,7 +648,8 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 			for (const FramePlan &fp : b->frames)
 				if (fp.n_blocks && fp.first_block + fp.n_blocks - 1 == b->presize[i]) { owner = &fp; break; }
 			const uint32_t bm = owner ? owner->block_max : 0xffffffffu;
-			sized[i] = std::min(ps[i].out_len, bm);   // a longer block fails in K1 anyway
+			// a block K5 cannot walk to its end keeps its block-maximum slot: K1 reports what is wrong with it
+			sized[i] = ps[i].code == LZ4B200_ST_OK ? std::min(ps[i].out_len, bm) : (b->exact_sizing ? 0xffffffffu : std::min(ps[i].out_len, bm));
 		}
 		const uint64_t upper = b->out_bytes;
 		place(b, &sized);

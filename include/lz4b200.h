@@ -367,6 +367,17 @@ void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read,
  * launching stream: ms[0] = K1 (independent blocks), ms[1] = K4 (chains), ms[2] = K3 (content
  * checksums).  0 for a kernel that did not run. */
 int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3]);
+
+/* Exact sizing: call between lz4ada_batch_plan and lz4ada_batch_upload.
+ * The upload then runs the size pre-pass K5 over every block of the independent-block frames and
+ * places the blocks back to back at their true sizes instead of one block-maximum apart: the output
+ * of a stream is contiguous from the first run on, so frames with short interior blocks (writers that
+ * flush often) never need the decode-again-as-a-chain retry.  lz4ada_batch_output_bytes keeps
+ * reporting the upper bound the caller allocated from.  Costs one extra pass over the compressed
+ * bytes (one thread per block). */
+int lz4ada_batch_exact_sizing(lz4ada_batch *b);
+/* How many streams the last run had to decode a second time as chains with exact placement. */
+uint32_t lz4ada_batch_retried_streams(const lz4ada_batch *b);
 /* Device stage: upload the tables (and the compressed bytes unless they are
  * already on the device), run K1..K4, fetch statuses and fold them in stream
  * order.  src_dev / dst_dev are device pointers sized src_bytes(+32 slack) /

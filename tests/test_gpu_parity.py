@@ -279,6 +279,40 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
         assert out == oout, stem
 
 
+
+def test_batch_exact_sizing(ctx, oracle):
+    """Exact sizing (K5 over every block, blocks placed back to back): same outcomes as the default placement for
+    good vectors, synthetic frames and corrupted streams; frames with short interior blocks no longer go through
+    the decode-again-as-a-chain retry."""
+    streams = [_read(s + ".lz4") for s in GOOD]
+    for stem, (exc, out, eof, msg) in zip(GOOD, lz.batch_decompress(ctx, streams, exact_sizing=True)):
+        assert exc == "OK", (stem, msg)
+        _check_output(stem, out)
+    cases = _synthetic_frames()
+    frames = [c[1] for c in cases]
+    i0, i1 = {}, {}
+    plain_res = lz.batch_decompress(ctx, frames, info=i0)
+    exact_res = lz.batch_decompress(ctx, frames, exact_sizing=True, info=i1)
+    assert plain_res == exact_res
+    for (name, frame, plain), (exc, out, eof, msg) in zip(cases, exact_res):
+        assert exc == "OK" and out == plain, (name, msg)
+    # the short-interior-blocks case needs the retry by default, never with exact sizing; linked frames that reach
+    # into the previous block are chains either way
+    text = corpus.text_like(300000, seed=3)
+    short = [corpus.build_frame(text, 4, False, True, block_size=50000), corpus.build_frame(text[:170000], 4, True, True, block_size=30000)]
+    j0, j1 = {}, {}
+    r0 = lz.batch_decompress(ctx, short, info=j0)
+    r1 = lz.batch_decompress(ctx, short, exact_sizing=True, info=j1)
+    assert r0 == r1 and r1[0][1] == text and r1[1][1] == text[:170000]
+    assert j0["retried_streams"] == 2 and j1["retried_streams"] == 0, (j0, j1)
+    # corrupted streams: the same exception, message and bytes-before-error as the oracle
+    rng = np.random.default_rng(17)
+    mix = text[:60000] + bytes(5000) + corpus.random_bytes(3000, seed=1) + text[60000:120000]
+    bad = _mutations(corpus.build_frame(mix, 4, True, True, True), rng, 40) + _mutations(short[0], rng, 20)
+    for k, (data, (exc, out, eof, msg)) in enumerate(zip(bad, lz.batch_decompress(ctx, bad, exact_sizing=True))):
+        oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 21)
+        assert (exc, msg, out) == (oexc, omsg, oout), (k, exc, msg, oexc, omsg)
+
 @pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64, 40, 41, 48, 50])
 def test_batch_k1_variants(ctx, oracle, g):
     """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8/16 blocks per warp, 64 = v3 CTA per block,
