@@ -335,7 +335,7 @@ def run_ours(args):
 
     traffic = batch.traffic()
     peak, peak_src = peaks()
-    k1_name = ctx.k1_kernel_name(batch.block_count)
+    k1_name = batch.k1_kernel_name() or ctx.k1_kernel_name(batch.block_count)
     k1 = float(np.mean(k1_ms)) if k1_ms else 0.0
     k1_bytes = traffic["compressed_read"] + traffic["decompressed_written"]
     achieved = k1_bytes / (k1 / 1e3) / 1e9 if k1 > 0 else 0.0

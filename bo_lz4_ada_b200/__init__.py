@@ -205,6 +205,7 @@ _SIGNATURES = {
     "lz4ada_batch_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "lz4ada_batch_exact_sizing": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4ada_batch_retried_streams": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "lz4ada_batch_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p]),
     "lz4ada_batch_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4ada_batch_run_pipelined": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -526,6 +527,10 @@ class Batch:
 
     def retried_streams(self):
         return lib().lz4ada_batch_retried_streams(self._h)
+
+    def k1_kernel_name(self):
+        """The K1 kernel the last run() launched."""
+        return lib().lz4ada_batch_k1_kernel_name(self._h).decode()
 
     def kernel_ms(self):
         """Device time of K1 / K4 / K3 in the last run (CUDA events on the launching stream)."""

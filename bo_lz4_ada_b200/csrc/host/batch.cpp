@@ -133,6 +133,8 @@ struct lz4ada_batch {
 	std::vector<lz4b200_chain> chains;
 	std::vector<lz4b200_frame_blocks> hash_frames;   // frames whose content checksum K3 computes
 	bool exact_sizing = false;                       // lz4ada_batch_exact_sizing: K5 sizes every block first
+	int64_t heavy_blocks = -1;                       // blocks that take long to decode (K1 kernel choice), -1 = not counted yet
+	const char *k1_name = "";                        // the K1 kernel the last lz4ada_batch_run launched
 	std::vector<uint32_t> presize;                   // blocks K5 sizes before placement
 	std::vector<uint32_t> sized;                     // their sizes once K5 has run
 	bool have_sized = false;
@@ -590,6 +592,8 @@ int lz4ada_batch_exact_sizing(lz4ada_batch *b)
 	return LZ4ADA_OK;
 }
 
+const char *lz4ada_batch_k1_kernel_name(const lz4ada_batch *b) { return b ? b->k1_name : ""; }
+
 uint32_t lz4ada_batch_retried_streams(const lz4ada_batch *b)
 {
 	uint32_t n = 0;
@@ -698,7 +702,31 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 		for (void *&e : b->ev)
 			if (!e && lz4b200_event_create(ctx, &e) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		lz4b200_event_record(ctx, b->ev[0]);
-		if (lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(nb), b->d_desc, b->d_status) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		{
+			// K1's own rule picks the lane-per-block kernel (v5) from the block count alone.  What fills its 75 776
+			// lanes, though, are the blocks that take long -- compressed ones of some size; stored blocks and RLE-like
+			// ones are over in microseconds and park a whole warp meanwhile.  With too few long blocks every lane
+			// decodes at most one and the launch lasts as long as that block (2 GiB of thirds text / RLE / random in
+			// 64 KiB blocks: 17.5 ms with v5, 5.6 ms with v4), so the host, which has the table, decides.
+			if (b->heavy_blocks < 0) {
+				int64_t n_heavy = 0;
+				for (const lz4b200_blk_desc &d : b->descs)
+					if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_CHAINED | LZ4B200_BLK_HASH_ONLY)) && d.src_len >= 4096 &&
+					    uint64_t(d.src_len) * 16 >= d.dst_cap)
+						n_heavy++;
+				b->heavy_blocks = n_heavy;
+			}
+			const uint64_t heavy = uint64_t(b->heavy_blocks);
+			const int sms = lz4b200_sm_count(ctx) > 0 ? lz4b200_sm_count(ctx) : 148;
+			const uint64_t lanes = uint64_t(sms) * 16 * 32;
+			const int saved_tuning = lz4b200_get_tuning(ctx);
+			const bool force_v4 = saved_tuning == 0 && heavy < lanes / 2 + lanes / 8;
+			if (force_v4) lz4b200_set_tuning(ctx, 40);
+			b->k1_name = lz4b200_k1_kernel_name(ctx, uint32_t(nb));
+			const int rc1 = lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(nb), b->d_desc, b->d_status);
+			if (force_v4) lz4b200_set_tuning(ctx, saved_tuning);
+			if (rc1 != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		}
 		lz4b200_event_record(ctx, b->ev[1]);
 		if (nc && lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(nc), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK)
 			return LZ4ADA_DEVICE_ERROR;

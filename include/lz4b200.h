@@ -376,6 +376,9 @@ int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3]);
  * reporting the upper bound the caller allocated from.  Costs one extra pass over the compressed
  * bytes (one thread per block). */
 int lz4ada_batch_exact_sizing(lz4ada_batch *b);
+/* Name of the K1 kernel the last lz4ada_batch_run launched (the batch scheduler overrides K1's
+ * block-count rule when too few of the blocks are long-running ones). */
+const char *lz4ada_batch_k1_kernel_name(const lz4ada_batch *b);
 /* How many streams the last run had to decode a second time as chains with exact placement. */
 uint32_t lz4ada_batch_retried_streams(const lz4ada_batch *b);
 /* Device stage: upload the tables (and the compressed bytes unless they are

@@ -56,7 +56,7 @@ def main():
         k1 = float(np.mean([m["k1_decode_blocks"] for m in ms[1:]]))
         k4 = float(np.mean([m.get("k4_decode_linked", 0.0) for m in ms[1:]]))
         k3 = float(np.mean([m["k3_xxh32_frames"] for m in ms[1:]]))
-        print(json.dumps({"tuning": t, "blocks": int(batch.block_count), "plain_bytes": plain, "ok": not bad and plain == c["plain_bytes"],
+        print(json.dumps({"tuning": t, "kernel": batch.k1_kernel_name(), "blocks": int(batch.block_count), "plain_bytes": plain, "ok": not bad and plain == c["plain_bytes"],
                           "k1_ms": k1, "k4_ms": k4, "k3_ms": k3, "k1_GBps_out": plain / (k1 / 1e3) / 1e9 if k1 else 0,
                           "k1_alg_GBps": (plain + n_src) / (k1 / 1e3) / 1e9 if k1 else 0}), flush=True)
     ctx.set_tuning(0)
