@@ -88,7 +88,7 @@ decode_blocks_v4_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 	extern __shared__ __align__(16) uint8_t v4_smem[];
 	v4::WarpMem *wms = reinterpret_cast<v4::WarpMem *>(v4_smem);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t first = (blockIdx.x * v4::WARPS + warp) * G;
+	const uint32_t first = (blockIdx.x * (blockDim.x >> 5) + warp) * G;   // 1 or v4::WARPS warps per CTA
 	if (first >= n_blocks) return;
 	v4::decode_group(src, dst, n_blocks, first, G, desc, status, wms[warp], lane);
 }
@@ -1079,9 +1079,17 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 			G = n_blocks >= 8 * per ? 8 : n_blocks >= 4 * per ? 4 : n_blocks >= 2 * per ? 2 : 1;
 		}
 		const uint32_t warps = (n_blocks + G - 1) / G;
-		const uint32_t grid = (warps + v4::WARPS - 1) / v4::WARPS;
-		decode_blocks_v4_kernel<<<grid, v4::WARPS * 32, v4::WARPS * sizeof(v4::WarpMem), ctx->stream>>>(src, dst, n_blocks, desc,
-														status, G);
+		// A CTA only leaves the SM when all its warps are done, and blocks differ wildly in how long they take (a
+		// 4 MiB text block 40 ms, an RLE or stored one microseconds): with four warps per CTA the 16 GiB mixed corpus
+		// (4096 blocks) ran in two waves, every CTA held hostage by its one text block.  Few warps => one per CTA;
+		// many (small blocks, short-lived) => four per CTA, which launches faster.  LZ4B200_V4_WARPS=1|4 forces it.
+		static const int wpc_env = [] {
+			const char *e = getenv("LZ4B200_V4_WARPS");
+			return e ? (e[0] == '4' ? int(v4::WARPS) : 1) : 0;
+		}();
+		const int wpc = wpc_env ? wpc_env : (warps <= 8192u ? 1 : int(v4::WARPS));
+		const uint32_t grid = (warps + wpc - 1) / wpc;
+		decode_blocks_v4_kernel<<<grid, wpc * 32, wpc * sizeof(v4::WarpMem), ctx->stream>>>(src, dst, n_blocks, desc, status, G);
 		ctx->launches++;
 		CK(cudaGetLastError());
 		return LZ4B200_OK;
