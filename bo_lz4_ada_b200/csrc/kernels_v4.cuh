@@ -32,7 +32,7 @@
 namespace lz4b200 {
 namespace v4 {
 
-constexpr int WARPS = 4;                     // per CTA
+constexpr int WARPS = 4;                     // per CTA at most (the launch uses one warp per CTA for batches of few, long-running blocks)
 constexpr uint32_t SEG = 132;                // 33 words: lane j's segment starts in bank j
 constexpr uint32_t WIN = 32 * SEG;           // compressed window per warp
 constexpr uint32_t CW_BYTES = WIN + 48;
