@@ -167,10 +167,16 @@ __device__ __forceinline__ uint32_t quad_xxh32(const uint8_t *p, uint64_t n, int
 // cp.async (LDGSTS, 16 bytes per lane, eight 256-byte groups in flight per quad = 8 MB in flight
 // for 4096 frames) and folds stripes straight out of shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t XXH_RING_BYTES = 2048;            // per quad
-constexpr uint32_t XXH_GROUP_BYTES = 256;            // 4 x (4 lanes x 16 B)
-constexpr uint32_t XXH_GROUPS = XXH_RING_BYTES / XXH_GROUP_BYTES;
+constexpr uint32_t XXH_GROUPS = 8;                   // cp.async groups in flight per quad
+constexpr uint32_t XXH_GROUP_BYTES = 256;            // 4 x (4 lanes x 16 B): the default group, 2 KiB ring per quad
+constexpr uint32_t XXH_RING_BYTES = XXH_GROUPS * XXH_GROUP_BYTES;
 constexpr uint32_t XXH_RING_STRIDE = XXH_RING_BYTES + 16;   // 16-byte skew per quad: conflict-free LDS
+// few, long spans (a handful of 4 MiB frames): the same ring with 1 KiB groups = 8 KiB in flight per quad
+constexpr uint32_t XXH_BIG_GROUP_BYTES = 1024;
+constexpr uint32_t XXH_BIG_RING_STRIDE = XXH_GROUPS * XXH_BIG_GROUP_BYTES + 16;
+// ... and when there is at most one warp per SM, 2 KiB groups = 16 KiB in flight per quad (131 KB per warp)
+constexpr uint32_t XXH_HUGE_GROUP_BYTES = 2048;
+constexpr uint32_t XXH_HUGE_RING_STRIDE = XXH_GROUPS * XXH_HUGE_GROUP_BYTES + 16;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -180,62 +186,67 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// All 32 lanes call this together; ring = this warp's 8 x XXH_RING_STRIDE bytes of shared memory.
-__device__ __forceinline__ uint32_t quad_xxh32_stream(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
+// All 32 lanes call this together; ring = this warp's 8 x (8 * GROUP_BYTES + 16) bytes of shared memory.
+template <uint32_t GROUP_BYTES>
+__device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
 {
+	constexpr uint32_t RING_BYTES = XXH_GROUPS * GROUP_BYTES;
+	constexpr uint32_t RING_STRIDE = RING_BYTES + 16;
+	constexpr uint32_t BATCH = GROUP_BYTES / 16;   // stripes per group
 	const int sub = lane & 3, q = lane >> 2;
-	uint8_t *my_ring = ring + q * XXH_RING_STRIDE;
+	uint8_t *my_ring = ring + q * RING_STRIDE;
 	const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(my_ring);
 	const uint64_t nstripes = n >> 4;
 	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
 	const uint32_t mis = static_cast<uint32_t>(a & 15);
 	const uint8_t *abase = p - mis;                                   // 16-byte aligned
 	const uint64_t need = nstripes ? mis + (nstripes << 4) + 4 : 0;    // bytes from abase the stripes touch
-	const uint32_t my_groups = static_cast<uint32_t>((need + XXH_GROUP_BYTES - 1) / XXH_GROUP_BYTES);
+	const uint32_t my_groups = static_cast<uint32_t>((need + GROUP_BYTES - 1) / GROUP_BYTES);
 	const uint32_t max_groups = __reduce_max_sync(FULL_MASK, my_groups);
 	const uint32_t sh = (mis & 3) * 8;
 	uint32_t acc = xxh_init_acc(sub);
 
 	auto issue = [&](uint32_t g) {
 		if (g < my_groups) {
-			const uint64_t gb = static_cast<uint64_t>(g) * XXH_GROUP_BYTES;
-			uint8_t *slot = my_ring + (gb & (XXH_RING_BYTES - 1));
+			const uint64_t gb = static_cast<uint64_t>(g) * GROUP_BYTES;
+			uint8_t *slot = my_ring + (gb & (RING_BYTES - 1));
 #pragma unroll
-			for (int c = 0; c < 4; c++) cp_async16(slot + c * 64 + sub * 16, abase + gb + c * 64 + sub * 16);
+			for (uint32_t c = 0; c < GROUP_BYTES / 64; c++) cp_async16(slot + c * 64 + sub * 16, abase + gb + c * 64 + sub * 16);
 		}
 		cp_async_commit();
 	};
 	for (uint32_t g = 0; g < XXH_GROUPS; g++) issue(g);
-	// Iteration g runs once group g has landed and folds stripe batch g - 1 (16 stripes = 256 bytes):
+	// Iteration g runs once group g has landed and folds stripe batch g - 1 (BATCH stripes = one group):
 	// lagging by one group means the bytes a misaligned span spills into the next group are there.
-	const uint64_t n_batches = (nstripes + 15) >> 4;
-	constexpr uint32_t WMASK = XXH_RING_BYTES / 4 - 1;
+	const uint64_t n_batches = (nstripes + BATCH - 1) / BATCH;
+	constexpr uint32_t WMASK = RING_BYTES / 4 - 1;
 	for (uint32_t g = 0; g <= max_groups; g++) {
 		// commits so far: 8 (prologue) + (g - 1); all but the newest 6 are complete => groups 0..g landed
 		cp_async_wait<XXH_GROUPS - 2>();
 		__syncwarp();
 		if (g >= 1 && g - 1 < n_batches) {
-			const uint64_t s0 = static_cast<uint64_t>(g - 1) << 4;
+			const uint64_t s0 = static_cast<uint64_t>(g - 1) * BATCH;
 			const uint32_t w0 = static_cast<uint32_t>((mis + (s0 << 4) + (sub << 2)) >> 2);   // word index, unwrapped
-			if (nstripes - s0 >= 16) {
+			const uint64_t left = nstripes - s0;
+			const uint32_t cnt = left < BATCH ? static_cast<uint32_t>(left) : BATCH;
+			uint32_t j0 = 0;
+			for (; j0 + 16 <= cnt; j0 += 16) {
 				uint32_t x[16];
 				if (sh == 0) {
 #pragma unroll
-					for (int j = 0; j < 16; j++) x[j] = ring32[(w0 + 4 * j) & WMASK];
+					for (int j = 0; j < 16; j++) x[j] = ring32[(w0 + 4 * (j0 + j)) & WMASK];
 				} else {
 #pragma unroll
 					for (int j = 0; j < 16; j++)
-						x[j] = __funnelshift_r(ring32[(w0 + 4 * j) & WMASK], ring32[(w0 + 4 * j + 1) & WMASK], sh);
+						x[j] = __funnelshift_r(ring32[(w0 + 4 * (j0 + j)) & WMASK], ring32[(w0 + 4 * (j0 + j) + 1) & WMASK], sh);
 				}
 #pragma unroll
 				for (int j = 0; j < 16; j++) acc = xxh_round(acc, x[j]);
-			} else {
-				const uint32_t cnt = static_cast<uint32_t>(nstripes - s0);
-				for (uint32_t j = 0; j < cnt; j++) {
-					uint32_t x = ring32[(w0 + 4 * j) & WMASK];
-					if (sh) x = __funnelshift_r(x, ring32[(w0 + 4 * j + 1) & WMASK], sh);
-					acc = xxh_round(acc, x);
-				}
+			}
+			for (uint32_t j = j0; j < cnt; j++) {
+				uint32_t x = ring32[(w0 + 4 * j) & WMASK];
+				if (sh) x = __funnelshift_r(x, ring32[(w0 + 4 * j + 1) & WMASK], sh);
+				acc = xxh_round(acc, x);
 			}
 		}
 		__syncwarp();
@@ -247,6 +258,11 @@ __device__ __forceinline__ uint32_t quad_xxh32_stream(const uint8_t *p, uint64_t
 	const uint32_t a2 = __shfl_sync(FULL_MASK, acc, 2, 4);
 	const uint32_t a3 = __shfl_sync(FULL_MASK, acc, 3, 4);
 	return xxh_finish<true>(a0, a1, a2, a3, n, p + (nstripes << 4), static_cast<uint32_t>(n & 15));
+}
+
+__device__ __forceinline__ uint32_t quad_xxh32_stream(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
+{
+	return quad_xxh32_stream_t<XXH_GROUP_BYTES>(p, n, ring, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

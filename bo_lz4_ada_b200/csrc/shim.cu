@@ -604,6 +604,7 @@ xxh32_spans_kernel(const uint8_t *__restrict__ data, uint32_t n,
 }
 
 // K3 (batch): content checksum per frame, length summed from the block statuses on the device.
+template <uint32_t GROUP_BYTES>
 __global__ void __launch_bounds__(128)
 xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 		    const lz4b200_frame_blocks *__restrict__ frames,
@@ -632,8 +633,8 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 	}
 	if (!okay) len = 0;
 	extern __shared__ uint4 xxh_rings[];
-	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * XXH_RING_STRIDE);
-	const uint32_t h = quad_xxh32_stream(dst + base, len, ring, lane);
+	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * (XXH_GROUPS * GROUP_BYTES + 16));
+	const uint32_t h = quad_xxh32_stream_t<GROUP_BYTES>(dst + base, len, ring, lane);
 	if (have && (lane & 3) == 0) {
 		digest[f] = h;
 		valid[f] = okay ? 1u : 0u;
@@ -824,7 +825,11 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 	{
 		// once per context, not per launch: the K3 kernels need > 48 KiB of dynamic shared memory
 		const int smem = 4 * 8 * XXH_RING_STRIDE;
-		cudaFuncSetAttribute(xxh32_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(xxh32_frames_kernel<XXH_GROUP_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(xxh32_frames_kernel<XXH_BIG_GROUP_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(8 * XXH_BIG_RING_STRIDE));
+		cudaFuncSetAttribute(xxh32_frames_kernel<XXH_HUGE_GROUP_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(8 * XXH_HUGE_RING_STRIDE));
 		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(decode_blocks_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v3::SMEM_BYTES));
 		cudaFuncSetAttribute(decode_blocks_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1147,9 +1152,21 @@ int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_frames == 0) return LZ4B200_OK;
 	const uint32_t warps = (n_frames + 7) / 8;
-	const size_t smem = 4 * 8 * XXH_RING_STRIDE;
-	xxh32_frames_kernel<<<(warps + 3) / 4, 128, smem, ctx->stream>>>(dst, n_frames, frames, desc, status, digest,
-									  valid);
+	// A chain needs 16 bytes every ~14 cycles and a quad can only keep its ring in flight.  With thousands of
+	// frames the sum is plenty (4096 frames x 2 KiB: 2.9 TB/s); with few, long ones (1024 frames of 4 MiB: one
+	// warp per SM) the 2 KiB ring is the limit (0.75 TB/s), so those get 8 or 16 KiB rings, one warp per CTA.
+	const uint32_t sms = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148);
+	if (warps <= sms) {
+		xxh32_frames_kernel<XXH_HUGE_GROUP_BYTES><<<warps, 32, 8 * XXH_HUGE_RING_STRIDE, ctx->stream>>>(dst, n_frames, frames, desc,
+														status, digest, valid);
+	} else if (warps <= 3 * sms) {
+		xxh32_frames_kernel<XXH_BIG_GROUP_BYTES><<<warps, 32, 8 * XXH_BIG_RING_STRIDE, ctx->stream>>>(dst, n_frames, frames, desc,
+													      status, digest, valid);
+	} else {
+		const size_t smem = 4 * 8 * XXH_RING_STRIDE;
+		xxh32_frames_kernel<XXH_GROUP_BYTES><<<(warps + 3) / 4, 128, smem, ctx->stream>>>(dst, n_frames, frames, desc, status,
+												   digest, valid);
+	}
 	ctx->launches++;
 	CK(cudaGetLastError());
 	return LZ4B200_OK;
