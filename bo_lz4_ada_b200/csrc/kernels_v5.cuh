@@ -67,35 +67,38 @@ __device__ __forceinline__ uint32_t col(uint32_t x, uint32_t lane4)
 }
 
 // n <= 32 bytes from registers into the lane's out ring at position d.  maxn = warp-uniform bound on n.
+// A ring column belongs to one lane, so partial words need no byte stores: the first word is merged with the
+// bytes already in front of d (read-modify-write), every further word is stored whole.  Bytes behind d + n in the
+// last word are clobbered unless KEEP_TAIL: behind a literal run nothing has been written yet (a match piece
+// whose literals were written first -- the deferred copy -- must keep them).
+template <bool KEEP_TAIL>
 __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const Bytes36 &D, uint32_t d, uint32_t n, uint32_t maxn,
 					    bool active)
 {
 	if (!active) return;
 	constexpr uint32_t M = OWW * 128 - 1;
-	const uint32_t hb0 = (4u - (d & 3u)) & 3u;
-	const uint32_t hb = hb0 < n ? hb0 : n;   // head bytes up to the next word boundary
-	uint8_t *hp = outb + col<OWW>(d, lane4);
-	if (hb > 0) hp[0] = static_cast<uint8_t>(D.w[0]);
-	if (hb > 1) hp[1] = static_cast<uint8_t>(D.w[0] >> 8);
-	if (hb > 2) hp[2] = static_cast<uint8_t>(D.w[0] >> 16);
-	const uint32_t hs = hb * 8;
-	const uint32_t nwords = (n - hb) >> 2;
-	const uint32_t u0 = ((((d + hb) >> 2) << 7) | lane4);   // first full word
-	uint32_t tail = 0;
+	const uint32_t s8 = (d & 3u) * 8u;                    // bit position of byte d in its word
+	const uint32_t nw = ((d & 3u) + n + 3u) >> 2;         // words touched, 1..9
+	const uint32_t u0 = ((d >> 2) << 7) | lane4;
+	uint32_t *first = reinterpret_cast<uint32_t *>(outb + (u0 & M));
+	uint32_t *lastp = reinterpret_cast<uint32_t *>(outb + ((u0 + (nw - 1) * 128) & M));
+	const uint32_t end8 = ((d + n) & 3u) * 8u;            // valid bits of the last word (0 = all 32)
+	uint32_t old_last = 0;
+	if (KEEP_TAIL && end8) old_last = *lastp;
+	// word 0: payload shifted up to byte d, the bytes in front of d kept
+	const uint32_t old0 = *first;
+	const uint32_t low = s8 ? (0xffffffffu >> (32u - s8)) : 0u;
+	*first = (D.w[0] << s8) | (old0 & low);
 #pragma unroll
-	for (int j = 0; j < 8; j++) {
-		if (static_cast<uint32_t>(j * 4) < maxn) {
-			const uint32_t v = __funnelshift_r(D.w[j], D.w[j + 1], hs);
-			if (static_cast<uint32_t>(j) < nwords) *reinterpret_cast<uint32_t *>(outb + ((u0 + j * 128) & M)) = v;
-			if (static_cast<uint32_t>(j) == nwords) tail = v;
+	for (int j = 1; j < 9; j++) {
+		if (static_cast<uint32_t>(j * 4) < maxn + 4u) {
+			if (static_cast<uint32_t>(j) < nw)
+				*reinterpret_cast<uint32_t *>(outb + ((u0 + j * 128) & M)) = __funnelshift_l(D.w[j - 1], D.w[j], s8);
 		}
 	}
-	const uint32_t tb = hb + 4u * nwords;
-	if (tb < n) {
-		uint8_t *tp = outb + ((u0 + nwords * 128) & M);
-		tp[0] = static_cast<uint8_t>(tail);
-		if (tb + 1 < n) tp[1] = static_cast<uint8_t>(tail >> 8);
-		if (tb + 2 < n) tp[2] = static_cast<uint8_t>(tail >> 16);
+	if (KEEP_TAIL && end8) {
+		const uint32_t keep = 0xffffffffu << end8;        // bytes behind d + n
+		*lastp = (*lastp & ~keep) | (old_last & keep);
 	}
 }
 
@@ -426,7 +429,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
 			if (maxn) {
 				fetch_col<IWW>(D, inb, lane4, a_cur, n, maxn, n != 0);
-				store_bytes(outb, lane4, D, p_cur, n, maxn, n != 0);
+				store_bytes<false>(outb, lane4, D, p_cur, n, maxn, n != 0);
 				if (n) {
 					a_cur += n;
 					p_cur += n;
@@ -534,7 +537,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				const bool is_far = n != 0 && pend_far, is_near = n != 0 && !pend_far;
 				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + pend_src, n, is_far);
 				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, pend_src, n, maxn, is_near);
-				store_bytes(outb, lane4, D, pend_dst, n, maxn, n != 0);
+				store_bytes<true>(outb, lane4, D, pend_dst, n, maxn, n != 0);
 				if (n) progressed = true;
 			}
 			pend_n = 0;
@@ -593,7 +596,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				const uint32_t src_s = p_cur - dist;
 				// what the ring still holds when the piece is copied: the next trip may write up to 16 literal bytes
 				// behind it first
-				const uint32_t hi = p_cur + n + LIT_PIECE;
+				const uint32_t hi = p_cur + n + LIT_PIECE + 4u;   // + the bytes a literal store clobbers behind its end
 				const uint32_t lo_wr = hi > OUT_BYTES ? hi - OUT_BYTES : 0u;
 				const uint32_t near_lo = ring_lo > lo_wr ? ring_lo : lo_wr;
 				pend_far = src_s < near_lo;
