@@ -89,11 +89,14 @@ __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const
 	const uint32_t old0 = *first;
 	const uint32_t low = s8 ? (0xffffffffu >> (32u - s8)) : 0u;
 	*first = (D.w[0] << s8) | (old0 & low);
+	// (the warp-uniform guard covers two words at a time: half the branches)
 #pragma unroll
-	for (int j = 1; j < 9; j++) {
-		if (static_cast<uint32_t>(j * 4) < maxn + 4u) {
-			if (static_cast<uint32_t>(j) < nw)
-				*reinterpret_cast<uint32_t *>(outb + ((u0 + j * 128) & M)) = __funnelshift_l(D.w[j - 1], D.w[j], s8);
+	for (int jj = 1; jj < 9; jj += 2) {
+		if (static_cast<uint32_t>(jj * 4) < maxn + 4u) {
+#pragma unroll
+			for (int j = jj; j < jj + 2; j++)
+				if (static_cast<uint32_t>(j) < nw)
+					*reinterpret_cast<uint32_t *>(outb + ((u0 + j * 128) & M)) = __funnelshift_l(D.w[j - 1], D.w[j], s8);
 		}
 	}
 	if (KEEP_TAIL && end8) {
@@ -114,10 +117,13 @@ __device__ __forceinline__ void fetch_col(Bytes36 &D, const uint8_t *ringb, uint
 	const uint32_t nw = (n + (s & 3u) + 3u) >> 2;   // words that hold payload
 	uint32_t x[10];
 #pragma unroll
-	for (int j = 0; j < 10; j++) {
-		x[j] = 0;
-		if (static_cast<uint32_t>(j * 4) < maxn + 4u) {
-			if (static_cast<uint32_t>(j) < nw) x[j] = *reinterpret_cast<const uint32_t *>(ringb + ((u0 + j * 128) & M));
+	for (int j = 0; j < 10; j++) x[j] = 0;
+#pragma unroll
+	for (int jj = 0; jj < 10; jj += 2) {
+		if (static_cast<uint32_t>(jj * 4) < maxn + 4u) {
+#pragma unroll
+			for (int j = jj; j < jj + 2; j++)
+				if (static_cast<uint32_t>(j) < nw) x[j] = *reinterpret_cast<const uint32_t *>(ringb + ((u0 + j * 128) & M));
 		}
 	}
 #pragma unroll
