@@ -87,7 +87,7 @@ __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const
 	if (KEEP_TAIL && end8) old_last = *lastp;
 	// word 0: payload shifted up to byte d, the bytes in front of d kept
 	const uint32_t old0 = *first;
-	const uint32_t low = s8 ? (0xffffffffu >> (32u - s8)) : 0u;
+	const uint32_t low = (1u << s8) - 1u;               // s8 is 0, 8, 16 or 24
 	*first = (D.w[0] << s8) | (old0 & low);
 	// (the warp-uniform guard covers two words at a time: half the branches)
 #pragma unroll
@@ -423,8 +423,6 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			}
 		}
 		// ================= stage 2: up to 16 literal bytes, in ring -> registers -> out ring (:790-824) =================
-#pragma unroll
-		for (int j = 0; j < 9; j++) D.w[j] = 0;
 		{
 			const uint32_t avail = have > a_cur ? have - a_cur : 0u;
 			uint32_t n = 0;
