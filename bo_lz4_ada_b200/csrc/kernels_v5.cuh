@@ -540,7 +540,9 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			if (maxn) {
 				const bool is_far = n != 0 && pend_far, is_near = n != 0 && !pend_far;
 				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + pend_src, n, is_far);
-				if (__any_sync(FULL_MASK, is_near)) fetch_col<OWW>(D, outb, lane4, pend_src, n, maxn, is_near);
+				// (the words to read follow from the longest *young* piece, usually much shorter than the longest piece)
+				const uint32_t maxnear = __reduce_max_sync(FULL_MASK, is_near ? n : 0u);
+				if (maxnear) fetch_col<OWW>(D, outb, lane4, pend_src, n, maxnear, is_near);
 				store_bytes<true>(outb, lane4, D, pend_dst, n, maxn, n != 0);
 				if (n) progressed = true;
 			}
