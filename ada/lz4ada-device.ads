@@ -100,5 +100,16 @@ private package LZ4Ada.Device is
      with Import, Convention => C, External_Name => "lz4b200_stream_block";
    function Stream_Digest (S : Stream; XXH32 : out Unsigned_32) return int
      with Import, Convention => C, External_Name => "lz4b200_stream_digest";
+   --  read-ahead under Update: N bytes decoded ahead of time by Decode_Blocks into a device staging buffer
+   --  become the stream's next bytes (history window + running content checksum)
+   function Stream_Adopt (S : Stream; Dev_Bytes : System.Address; N : Unsigned_32; Hash_Content : int) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_adopt";
+
+   --  which K1 kernel Decode_Blocks launches: 0 = chosen from the block count (v5 lane-per-block for batches that
+   --  fill the chip, v4 warp-per-block otherwise); see include/lz4b200.h for the other values
+   function Set_Tuning (Ctx : Context; Generation : int) return int
+     with Import, Convention => C, External_Name => "lz4b200_set_tuning";
+   function K1_Kernel_Name (Ctx : Context; N_Blocks : Unsigned_32) return Interfaces.C.Strings.chars_ptr
+     with Import, Convention => C, External_Name => "lz4b200_k1_kernel_name";
 
 end LZ4Ada.Device;
