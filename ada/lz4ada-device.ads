@@ -4,6 +4,7 @@
 --  errors never travel in the return code; they come back in Block_Status records.
 with Interfaces;   use Interfaces;
 with Interfaces.C; use Interfaces.C;
+with Interfaces.C.Strings;
 with System;
 
 private package LZ4Ada.Device is
