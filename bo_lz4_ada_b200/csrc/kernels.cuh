@@ -174,6 +174,9 @@ constexpr uint32_t XXH_RING_STRIDE = XXH_RING_BYTES + 16;   // 16-byte skew per 
 // few, long spans (a handful of 4 MiB frames): the same ring with 1 KiB groups = 8 KiB in flight per quad
 constexpr uint32_t XXH_BIG_GROUP_BYTES = 1024;
 constexpr uint32_t XXH_BIG_RING_STRIDE = XXH_GROUPS * XXH_BIG_GROUP_BYTES + 16;
+// a few warps per SM: 512-byte groups = 4 KiB in flight per quad (33 KB per warp, one warp per CTA)
+constexpr uint32_t XXH_MID_GROUP_BYTES = 512;
+constexpr uint32_t XXH_MID_RING_STRIDE = XXH_GROUPS * XXH_MID_GROUP_BYTES + 16;
 // ... and when there is at most one warp per SM, 2 KiB groups = 16 KiB in flight per quad (131 KB per warp)
 constexpr uint32_t XXH_HUGE_GROUP_BYTES = 2048;
 constexpr uint32_t XXH_HUGE_RING_STRIDE = XXH_GROUPS * XXH_HUGE_GROUP_BYTES + 16;

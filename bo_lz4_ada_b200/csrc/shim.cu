@@ -830,6 +830,8 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 				     int(8 * XXH_BIG_RING_STRIDE));
 		cudaFuncSetAttribute(xxh32_frames_kernel<XXH_HUGE_GROUP_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(8 * XXH_HUGE_RING_STRIDE));
+		cudaFuncSetAttribute(xxh32_frames_kernel<XXH_MID_GROUP_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(8 * XXH_MID_RING_STRIDE));
 		cudaFuncSetAttribute(xxh32_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		cudaFuncSetAttribute(decode_blocks_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(v3::SMEM_BYTES));
 		cudaFuncSetAttribute(decode_blocks_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1161,6 +1163,9 @@ int lz4b200_xxh32_frames(lz4b200_ctx *ctx, const uint8_t *dst, uint32_t n_frames
 														status, digest, valid);
 	} else if (warps <= 3 * sms) {
 		xxh32_frames_kernel<XXH_BIG_GROUP_BYTES><<<warps, 32, 8 * XXH_BIG_RING_STRIDE, ctx->stream>>>(dst, n_frames, frames, desc,
+													      status, digest, valid);
+	} else if (warps <= 6 * sms) {
+		xxh32_frames_kernel<XXH_MID_GROUP_BYTES><<<warps, 32, 8 * XXH_MID_RING_STRIDE, ctx->stream>>>(dst, n_frames, frames, desc,
 													      status, digest, valid);
 	} else {
 		const size_t smem = 4 * 8 * XXH_RING_STRIDE;
