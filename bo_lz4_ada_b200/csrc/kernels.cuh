@@ -31,6 +31,44 @@ __device__ __forceinline__ uint32_t xxh_round(uint32_t acc, uint32_t x)
 	return rotl32(acc + x * PRIME_2, 13) * PRIME_1;
 }
 
+// A run of rounds of ONE accumulator is a serial chain, and written as above every round is three dependent
+// operations (IMAD, SHF, IMAD: 14 cycles on sm_100a, the multiplier and the shifter sit on different pipes).
+// Carrying s = acc + x * P2 instead, a round is s' = rotl(s, 13) * P1 + x' * P2 with the product x' * P2 off the
+// chain: two dependent operations (SHF, IMAD).  LZ4B200_XXH_CHAIN = 2 goes one further: rotl(s, 13) = lo(s * 2^13) +
+// hi(s * 2^13), so s' = s * (P1 << 13) + hi(s * 2^13) * P1 + x' * P2 -- IMAD.HI, then IMAD, both on the multiplier
+// pipe (the 2^13 comes from constant memory so that it stays a multiplication).  Same integers either way.
+// Inline PTX because the compiler re-associates the sum and puts x' * P2 back on the chain otherwise.
+// Measured per round by tools/probes/xxh_chain_probe.cu.
+#ifndef LZ4B200_XXH_CHAIN
+#define LZ4B200_XXH_CHAIN 1
+#endif
+__constant__ uint32_t xxh_two13 = 8192u;
+
+__device__ __forceinline__ uint32_t xxh_step(uint32_t s, uint32_t x)
+{
+	uint32_t c, r;
+	asm("mul.lo.u32 %0, %1, %2;" : "=r"(c) : "r"(x), "r"(PRIME_2));
+#if LZ4B200_XXH_CHAIN == 2
+	uint32_t hi, a;
+	asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(s), "r"(xxh_two13));
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(s), "r"(PRIME_1 << 13), "r"(c));
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(PRIME_1), "r"(a));
+#else
+	const uint32_t t = rotl32(s, 13);
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(PRIME_1), "r"(c));
+#endif
+	return r;
+}
+
+// acc after N more rounds (Rot_Mul N times, lib/lz4ada.adb:982-985)
+template <int N> __device__ __forceinline__ uint32_t xxh_fold(uint32_t acc, const uint32_t (&x)[N])
+{
+	uint32_t s = acc + x[0] * PRIME_2;
+#pragma unroll
+	for (int j = 1; j < N; j++) s = xxh_step(s, x[j]);
+	return rotl32(s, 13) * PRIME_1;
+}
+
 // Loads.  RO = the bytes are never written during this kernel (compressed input, or output of an
 // earlier launch): non-coherent path.  Otherwise a plain load, ordered by __syncwarp().
 template <bool RO> __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p)
@@ -106,13 +144,11 @@ __device__ __forceinline__ uint32_t quad_stripes(const uint8_t *p, uint64_t nstr
 				for (int j = 0; j < 8; j++)
 					nxt[j] = __funnelshift_r(ld_u32<RO>(w + (s + j) * 4), ld_u32<RO>(w + (s + j) * 4 + 1), sh);
 			}
-#pragma unroll
-			for (int j = 0; j < 8; j++) acc = xxh_round(acc, cur[j]);
+			acc = xxh_fold<8>(acc, cur);
 #pragma unroll
 			for (int j = 0; j < 8; j++) cur[j] = nxt[j];
 		}
-#pragma unroll
-		for (int j = 0; j < 8; j++) acc = xxh_round(acc, cur[j]);
+		acc = xxh_fold<8>(acc, cur);
 	}
 	for (; s < nstripes; s++) {
 		const uint32_t x = mis == 0 ? ld_u32<RO>(w + s * 4)
@@ -168,18 +204,21 @@ __device__ __forceinline__ uint32_t quad_xxh32(const uint8_t *p, uint64_t n, int
 // for 4096 frames) and folds stripes straight out of shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t XXH_GROUPS = 8;                   // cp.async groups in flight per quad
+// behind each ring: 32 bytes that mirror its first 32 (a batch of stripes read from the last slot runs on linearly
+// into them), and 16 bytes of skew so that the eight quads of a warp start in different banks: conflict-free LDS
+constexpr uint32_t XXH_RING_PAD = 48;
 constexpr uint32_t XXH_GROUP_BYTES = 256;            // 4 x (4 lanes x 16 B): the default group, 2 KiB ring per quad
 constexpr uint32_t XXH_RING_BYTES = XXH_GROUPS * XXH_GROUP_BYTES;
-constexpr uint32_t XXH_RING_STRIDE = XXH_RING_BYTES + 16;   // 16-byte skew per quad: conflict-free LDS
+constexpr uint32_t XXH_RING_STRIDE = XXH_RING_BYTES + XXH_RING_PAD;
 // few, long spans (a handful of 4 MiB frames): the same ring with 1 KiB groups = 8 KiB in flight per quad
 constexpr uint32_t XXH_BIG_GROUP_BYTES = 1024;
-constexpr uint32_t XXH_BIG_RING_STRIDE = XXH_GROUPS * XXH_BIG_GROUP_BYTES + 16;
+constexpr uint32_t XXH_BIG_RING_STRIDE = XXH_GROUPS * XXH_BIG_GROUP_BYTES + XXH_RING_PAD;
 // a few warps per SM: 512-byte groups = 4 KiB in flight per quad (33 KB per warp, one warp per CTA)
 constexpr uint32_t XXH_MID_GROUP_BYTES = 512;
-constexpr uint32_t XXH_MID_RING_STRIDE = XXH_GROUPS * XXH_MID_GROUP_BYTES + 16;
+constexpr uint32_t XXH_MID_RING_STRIDE = XXH_GROUPS * XXH_MID_GROUP_BYTES + XXH_RING_PAD;
 // ... and when there is at most one warp per SM, 2 KiB groups = 16 KiB in flight per quad (131 KB per warp)
 constexpr uint32_t XXH_HUGE_GROUP_BYTES = 2048;
-constexpr uint32_t XXH_HUGE_RING_STRIDE = XXH_GROUPS * XXH_HUGE_GROUP_BYTES + 16;
+constexpr uint32_t XXH_HUGE_RING_STRIDE = XXH_GROUPS * XXH_HUGE_GROUP_BYTES + XXH_RING_PAD;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -189,21 +228,22 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// All 32 lanes call this together; ring = this warp's 8 x (8 * GROUP_BYTES + 16) bytes of shared memory.
+// All 32 lanes call this together; ring = this warp's 8 x (8 * GROUP_BYTES + XXH_RING_PAD) bytes of shared memory.
+// Reads whole 16-byte granules: at most 19 bytes past p + n (the batch API's 32 bytes of slack cover it).
 template <uint32_t GROUP_BYTES>
 __device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
 {
 	constexpr uint32_t RING_BYTES = XXH_GROUPS * GROUP_BYTES;
-	constexpr uint32_t RING_STRIDE = RING_BYTES + 16;
+	constexpr uint32_t RING_STRIDE = RING_BYTES + XXH_RING_PAD;
 	constexpr uint32_t BATCH = GROUP_BYTES / 16;   // stripes per group
 	const int sub = lane & 3, q = lane >> 2;
 	uint8_t *my_ring = ring + q * RING_STRIDE;
-	const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(my_ring);
 	const uint64_t nstripes = n >> 4;
 	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
 	const uint32_t mis = static_cast<uint32_t>(a & 15);
 	const uint8_t *abase = p - mis;                                   // 16-byte aligned
-	const uint64_t need = nstripes ? mis + (nstripes << 4) + 4 : 0;    // bytes from abase the stripes touch
+	// bytes from abase the stripes touch, in whole granules (+ 4: the word a misaligned last stripe spills into)
+	const uint64_t need = nstripes ? ((mis + (nstripes << 4) + 4 + 15) & ~uint64_t(15)) : 0;
 	const uint32_t my_groups = static_cast<uint32_t>((need + GROUP_BYTES - 1) / GROUP_BYTES);
 	const uint32_t max_groups = __reduce_max_sync(FULL_MASK, my_groups);
 	const uint32_t sh = (mis & 3) * 8;
@@ -212,9 +252,20 @@ __device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64
 	auto issue = [&](uint32_t g) {
 		if (g < my_groups) {
 			const uint64_t gb = static_cast<uint64_t>(g) * GROUP_BYTES;
-			uint8_t *slot = my_ring + (gb & (RING_BYTES - 1));
+			const uint32_t so = static_cast<uint32_t>(gb) & (RING_BYTES - 1);
+			uint8_t *slot = my_ring + so + sub * 16;
+			const uint8_t *gsrc = abase + gb + sub * 16;
+			if (gb + GROUP_BYTES <= need) {
 #pragma unroll
-			for (uint32_t c = 0; c < GROUP_BYTES / 64; c++) cp_async16(slot + c * 64 + sub * 16, abase + gb + c * 64 + sub * 16);
+				for (uint32_t c = 0; c < GROUP_BYTES / 64; c++) cp_async16(slot + c * 64, gsrc + c * 64);
+			} else {
+				// the span's last group: only the granules that belong to it
+#pragma unroll
+				for (uint32_t c = 0; c < GROUP_BYTES / 64; c++)
+					if (gb + c * 64 + sub * 16 < need) cp_async16(slot + c * 64, gsrc + c * 64);
+			}
+			// the mirror of the ring's first 32 bytes, behind its end
+			if (so == 0 && sub < 2 && gb + sub * 16 < need) cp_async16(my_ring + RING_BYTES + sub * 16, gsrc);
 		}
 		cp_async_commit();
 	};
@@ -222,34 +273,53 @@ __device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64
 	// Iteration g runs once group g has landed and folds stripe batch g - 1 (BATCH stripes = one group):
 	// lagging by one group means the bytes a misaligned span spills into the next group are there.
 	const uint64_t n_batches = (nstripes + BATCH - 1) / BATCH;
-	constexpr uint32_t WMASK = RING_BYTES / 4 - 1;
 	for (uint32_t g = 0; g <= max_groups; g++) {
 		// commits so far: 8 (prologue) + (g - 1); all but the newest 6 are complete => groups 0..g landed
 		cp_async_wait<XXH_GROUPS - 2>();
 		__syncwarp();
 		if (g >= 1 && g - 1 < n_batches) {
 			const uint64_t s0 = static_cast<uint64_t>(g - 1) * BATCH;
-			const uint32_t w0 = static_cast<uint32_t>((mis + (s0 << 4) + (sub << 2)) >> 2);   // word index, unwrapped
+			// this lane's word of stripe s0; stripe j is 4 j words further on -- linearly, also out of the last slot
+			// (whose spill is the mirror), so every load below is base + immediate
+			const uint32_t b0 = (((g - 1) * GROUP_BYTES) & (RING_BYTES - 1)) + (mis & ~3u) + (static_cast<uint32_t>(sub) << 2);
+			const uint32_t *w = reinterpret_cast<const uint32_t *>(my_ring + b0);
 			const uint64_t left = nstripes - s0;
-			const uint32_t cnt = left < BATCH ? static_cast<uint32_t>(left) : BATCH;
-			uint32_t j0 = 0;
-			for (; j0 + 16 <= cnt; j0 += 16) {
-				uint32_t x[16];
+			if (left >= BATCH) {
+				// a whole group, unrolled: the loads of the next 16 stripes are scheduled under the chain of these 16
 				if (sh == 0) {
 #pragma unroll
-					for (int j = 0; j < 16; j++) x[j] = ring32[(w0 + 4 * (j0 + j)) & WMASK];
+					for (uint32_t c = 0; c < BATCH / 16; c++) {
+						uint32_t x[16];
+#pragma unroll
+						for (int j = 0; j < 16; j++) x[j] = w[(c * 16 + j) * 4];
+						acc = xxh_fold<16>(acc, x);
+					}
 				} else {
 #pragma unroll
-					for (int j = 0; j < 16; j++)
-						x[j] = __funnelshift_r(ring32[(w0 + 4 * (j0 + j)) & WMASK], ring32[(w0 + 4 * (j0 + j) + 1) & WMASK], sh);
-				}
+					for (uint32_t c = 0; c < BATCH / 16; c++) {
+						uint32_t x[16];
 #pragma unroll
-				for (int j = 0; j < 16; j++) acc = xxh_round(acc, x[j]);
-			}
-			for (uint32_t j = j0; j < cnt; j++) {
-				uint32_t x = ring32[(w0 + 4 * j) & WMASK];
-				if (sh) x = __funnelshift_r(x, ring32[(w0 + 4 * j + 1) & WMASK], sh);
-				acc = xxh_round(acc, x);
+						for (int j = 0; j < 16; j++) x[j] = __funnelshift_r(w[(c * 16 + j) * 4], w[(c * 16 + j) * 4 + 1], sh);
+						acc = xxh_fold<16>(acc, x);
+					}
+				}
+			} else {
+				const uint32_t cnt = static_cast<uint32_t>(left);
+				uint32_t j0 = 0;
+				for (; j0 + 16 <= cnt; j0 += 16) {
+					uint32_t x[16];
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						x[j] = w[(j0 + j) * 4];
+						if (sh) x[j] = __funnelshift_r(x[j], w[(j0 + j) * 4 + 1], sh);
+					}
+					acc = xxh_fold<16>(acc, x);
+				}
+				for (uint32_t j = j0; j < cnt; j++) {
+					uint32_t x = w[j * 4];
+					if (sh) x = __funnelshift_r(x, w[j * 4 + 1], sh);
+					acc = xxh_round(acc, x);
+				}
 			}
 		}
 		__syncwarp();

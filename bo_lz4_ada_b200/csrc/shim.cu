@@ -633,7 +633,7 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 	}
 	if (!okay) len = 0;
 	extern __shared__ uint4 xxh_rings[];
-	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * (XXH_GROUPS * GROUP_BYTES + 16));
+	uint8_t *ring = reinterpret_cast<uint8_t *>(xxh_rings) + (threadIdx.x >> 5) * (8 * (XXH_GROUPS * GROUP_BYTES + XXH_RING_PAD));
 	const uint32_t h = quad_xxh32_stream_t<GROUP_BYTES>(dst + base, len, ring, lane);
 	if (have && (lane & 3) == 0) {
 		digest[f] = h;

@@ -491,6 +491,31 @@ def test_k3_xxh32_spans_alignment_and_lengths(ctx, oracle):
         ctx.free(p)
 
 
+@pytest.mark.parametrize("n_streams,len_a,len_b", [(8, 70001, 150003), (1200, 9001, 40010), (3600, 5003, 20005), (7200, 3001, 9007)])
+def test_k3_frames_ring_variants(ctx, n_streams, len_a, len_b):
+    """The content-checksum kernel picks its shared-memory ring by the number of frames (2 KiB groups for a handful
+    of frames down to 256-byte groups for thousands).  Every stream is two concatenated frames, so the second frame's
+    output starts at an arbitrary byte: misaligned spans that lap each ring several times, checked by the device
+    against the checksums in the frames (lib/lz4ada.adb:463-523) -- plus one frame with a wrong checksum."""
+    text = corpus.text_like(1 << 20, seed=11)
+    variants = []
+    for v in range(16):
+        a = text[v * 1009:][:len_a + v]
+        b = text[5000 + v * 4001:][:len_b + 3 * v]
+        variants.append((corpus.build_frame(a, 4, False, True) + corpus.build_frame(b, 4, True, True), a + b))
+    streams = [variants[i % 16][0] for i in range(n_streams)]
+    bad = bytearray(streams[n_streams // 2])
+    bad[-1] ^= 0x40   # the second frame's content checksum
+    streams[n_streams // 2] = bytes(bad)
+    res = lz.batch_decompress(ctx, streams)
+    for i, (exc, out, eof, msg) in enumerate(res):
+        if i == n_streams // 2:
+            assert exc == "CHECKSUM_ERROR" and "content checksum" in msg, (i, exc, msg)
+            continue
+        assert exc == "OK", (i, msg)
+        assert out == variants[i % 16][1], i
+
+
 def ctypes_sizeof(a):
     import ctypes
     return ctypes.sizeof(a)

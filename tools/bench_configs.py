@@ -68,6 +68,16 @@ def main():
         streams = [bytes(c["src"][o:o + l]) for o, l in c["items"]]
         results.append(run_case(ctx, "4MiB-blocks/" + "+".join(kinds), streams, c["plain"]))
         del c, streams
+    # the headline corpus as ONE frame (64 KiB blocks, block + content checksum): the content
+    # checksum is then a single serial XXH32 chain (K3 runs one quad), the decode is as parallel as before
+    if only and only in "one-frame":
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(16) as ex:
+            data = b"".join(ex.map(lambda i: corpus.text_like(64 << 20, seed=77 + i), range(max(1, int(16 * scale)))))
+        for cc in (True, False):
+            s = corpus.build_frame(data, 4, True, cc)
+            results.append(run_case(ctx, "one-frame/64KiB-blocks/%s" % ("content-checksum" if cc else "no-content-checksum"), [s], [data],
+                                    steps=2))
     if only:
         return
     # configs[3]: legacy frames, concatenated modern frames, skippable frames: batch of 1024 streams
