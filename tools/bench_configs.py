@@ -78,6 +78,15 @@ def main():
             s = corpus.build_frame(data, 4, True, cc)
             results.append(run_case(ctx, "one-frame/64KiB-blocks/%s" % ("content-checksum" if cc else "no-content-checksum"), [s], [data],
                                     steps=2))
+    # configs[4], second case: linked frames with 64 KiB blocks (every block leans on the whole previous one)
+    if only and only in "linked-64KiB-blocks/256-frames":
+        text64 = corpus.text_like(6 << 20, seed=5)
+        streams, plains = [], []
+        for i in range(int(256 * scale)):
+            p = text64[(i * 10007) % (2 << 20):][:2 << 20]
+            streams.append(corpus.build_frame(p, 4, True, True, True, independent=False))
+            plains.append(p)
+        results.append(run_case(ctx, "linked-64KiB-blocks/256-frames", streams, plains))
     if only:
         return
     # configs[3]: legacy frames, concatenated modern frames, skippable frames: batch of 1024 streams
