@@ -6,10 +6,11 @@
 // (lib/lz4ada.adb:155-361, 525-585) and a table {compressed offset, size, stored flag, checksum
 // flag} per block.  Nothing is decoded on the host.
 //
-// Device stage (lz4ada_batch_run): K1 over all independent blocks (one warp each), K4 over
-// linked frames (one warp per frame), K3 over the frames that carry a content checksum -- no host
-// round trip in between -- then one D2H of the status / digest arrays, folded in stream order
-// into the first exception the reference would have raised (SURVEY.md Appendix A "ordering").
+// Device stage (lz4ada_batch_run): K1 over all independent blocks (a lane or a warp per block,
+// chosen from the shape of the batch), K4 over linked frames (a CTA per chain), K3 over the frames
+// that carry a content checksum -- no host round trip in between -- then one D2H of the status /
+// digest arrays, folded in stream order into the first exception the reference would have raised
+// (SURVEY.md Appendix A "ordering").
 //
 // Output placement: the frame format has no per-block decompressed size.  Blocks are placed
 // optimistically at frame_base + i * block_max (true for every encoder that fills its blocks);
