@@ -66,19 +66,19 @@ __device__ __forceinline__ uint32_t col(uint32_t x, uint32_t lane4)
 	return (((x >> 2) & (W - 1)) << 7) + lane4 + (x & 3u);
 }
 
-// n <= 32 bytes from registers into the lane's out ring at position d.  maxn = warp-uniform bound on n.
+// n <= MAXB (16 or 32) bytes from registers into the lane's out ring at position d.  maxn = warp-uniform bound on n.
 // A ring column belongs to one lane, so partial words need no byte stores: the first word is merged with the
 // bytes already in front of d (read-modify-write), every further word is stored whole.  Bytes behind d + n in the
 // last word are clobbered unless KEEP_TAIL: behind a literal run nothing has been written yet (a match piece
 // whose literals were written first -- the deferred copy -- must keep them).
-template <bool KEEP_TAIL>
+template <bool KEEP_TAIL, uint32_t MAXB>
 __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const Bytes36 &D, uint32_t d, uint32_t n, uint32_t maxn,
 					    bool active)
 {
 	if (!active) return;
 	constexpr uint32_t M = OWW * 128 - 1;
 	const uint32_t s8 = (d & 3u) * 8u;                    // bit position of byte d in its word
-	const uint32_t nw = ((d & 3u) + n + 3u) >> 2;         // words touched, 1..9
+	const uint32_t nw = ((d & 3u) + n + 3u) >> 2;         // words touched, 1..MAXB / 4 + 1
 	const uint32_t u0 = ((d >> 2) << 7) | lane4;
 	uint32_t *first = reinterpret_cast<uint32_t *>(outb + (u0 & M));
 	uint32_t *lastp = reinterpret_cast<uint32_t *>(outb + ((u0 + (nw - 1) * 128) & M));
@@ -91,7 +91,7 @@ __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const
 	*first = (D.w[0] << s8) | (old0 & low);
 	// (the warp-uniform guard covers two words at a time: half the branches)
 #pragma unroll
-	for (int jj = 1; jj < 9; jj += 2) {
+	for (int jj = 1; jj < static_cast<int>(MAXB / 4 + 1); jj += 2) {
 		if (static_cast<uint32_t>(jj * 4) < maxn + 4u) {
 #pragma unroll
 			for (int j = jj; j < jj + 2; j++)
@@ -105,8 +105,9 @@ __device__ __forceinline__ void store_bytes(uint8_t *outb, uint32_t lane4, const
 	}
 }
 
-// n <= 32 bytes starting at position s of a lane's ring column into registers (byte 0 = position s).
-template <uint32_t W>
+// n <= MAXB (16 or 32) bytes starting at position s of a lane's ring column into registers (byte 0 = position s;
+// words 0 .. MAXB / 4 of D are written).
+template <uint32_t W, uint32_t MAXB>
 __device__ __forceinline__ void fetch_col(Bytes36 &D, const uint8_t *ringb, uint32_t lane4, uint32_t s, uint32_t n, uint32_t maxn,
 					  bool active)
 {
@@ -115,11 +116,12 @@ __device__ __forceinline__ void fetch_col(Bytes36 &D, const uint8_t *ringb, uint
 	const uint32_t bs = (s & 3u) * 8u;
 	const uint32_t u0 = ((s >> 2) << 7) | lane4;
 	const uint32_t nw = (n + (s & 3u) + 3u) >> 2;   // words that hold payload
-	uint32_t x[10];
+	constexpr int NX = MAXB / 4 + 2;   // words that can hold payload, + one for the shift
+	uint32_t x[NX];
 #pragma unroll
-	for (int j = 0; j < 10; j++) x[j] = 0;
+	for (int j = 0; j < NX; j++) x[j] = 0;
 #pragma unroll
-	for (int jj = 0; jj < 10; jj += 2) {
+	for (int jj = 0; jj < NX; jj += 2) {
 		if (static_cast<uint32_t>(jj * 4) < maxn + 4u) {
 #pragma unroll
 			for (int j = jj; j < jj + 2; j++)
@@ -127,7 +129,7 @@ __device__ __forceinline__ void fetch_col(Bytes36 &D, const uint8_t *ringb, uint
 		}
 	}
 #pragma unroll
-	for (int j = 0; j < 9; j++) D.w[j] = __funnelshift_r(x[j], x[j + 1], bs);
+	for (int j = 0; j < NX - 1; j++) D.w[j] = __funnelshift_r(x[j], x[j + 1], bs);
 }
 
 // 48 aligned bytes A|B|C whose payload starts at byte m -> registers (byte 0 = payload byte 0).
@@ -397,9 +399,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		const uint32_t have = a_loaded < a_end ? a_loaded : a_end;   // payload bytes are valid below this
 		const bool all_in = have == a_end;
 
-		Bytes36 D;
-#pragma unroll
-		for (int j = 0; j < 9; j++) D.w[j] = 0;
+		Bytes36 D;   // written by whichever fetch precedes a store; a lane that fetches nothing stores nothing
 		// ================= stage 1: token (Decompress_Sequence, lib/lz4ada.adb:737-750) =================
 		if (run && sq == S_TOKEN) {
 			const uint32_t avail = have > a_cur ? have - a_cur : 0u;
@@ -432,8 +432,8 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			}
 			const uint32_t maxn = __reduce_max_sync(FULL_MASK, n);
 			if (maxn) {
-				fetch_col<IWW>(D, inb, lane4, a_cur, n, maxn, n != 0);
-				store_bytes<false>(outb, lane4, D, p_cur, n, maxn, n != 0);
+				fetch_col<IWW, LIT_PIECE>(D, inb, lane4, a_cur, n, maxn, n != 0);
+				store_bytes<false, LIT_PIECE>(outb, lane4, D, p_cur, n, maxn, n != 0);
 				if (n) {
 					a_cur += n;
 					p_cur += n;
@@ -542,8 +542,8 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				if (__any_sync(FULL_MASK, is_far)) stage_take(D, slot, obase + pend_src, n, is_far);
 				// (the words to read follow from the longest *young* piece, usually much shorter than the longest piece)
 				const uint32_t maxnear = __reduce_max_sync(FULL_MASK, is_near ? n : 0u);
-				if (maxnear) fetch_col<OWW>(D, outb, lane4, pend_src, n, maxnear, is_near);
-				store_bytes<true>(outb, lane4, D, pend_dst, n, maxn, n != 0);
+				if (maxnear) fetch_col<OWW, ML_PIECE>(D, outb, lane4, pend_src, n, maxnear, is_near);
+				store_bytes<true, ML_PIECE>(outb, lane4, D, pend_dst, n, maxn, n != 0);
 				if (n) progressed = true;
 			}
 			pend_n = 0;
