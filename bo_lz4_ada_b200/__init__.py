@@ -131,6 +131,7 @@ class BatchResult(ctypes.Structure):  # lz4ada_batch_result
 _SIGNATURES = {
     # device shim
     "lz4b200_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "lz4b200_retain": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "lz4b200_sm_count": (ctypes.c_int, [ctypes.c_void_p]),
@@ -203,6 +204,7 @@ _SIGNATURES = {
     "lz4ada_batch_traffic": (None, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
                                     ctypes.POINTER(ctypes.c_uint64)]),
     "lz4ada_batch_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "lz4ada_batch_set_output_capacity": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "lz4ada_batch_exact_sizing": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4ada_batch_retried_streams": (ctypes.c_uint32, [ctypes.c_void_p]),
     "lz4ada_batch_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p]),
@@ -525,6 +527,10 @@ class Batch:
         if lib().lz4ada_batch_exact_sizing(self._h) != 0:
             raise Assertion_Error("raised LZ4ADA.ASSERTION_ERROR : exact_sizing after upload")
 
+    def set_output_capacity(self, nbytes):
+        """Tell the batch how large the output buffer really is (room for streams that outgrow their region)."""
+        lib().lz4ada_batch_set_output_capacity(self._h, nbytes)
+
     def retried_streams(self):
         return lib().lz4ada_batch_retried_streams(self._h)
 
@@ -568,8 +574,10 @@ def batch_decompress(ctx, streams, Reservation="For_All", exact_sizing=False, in
     if exact_sizing:
         b.exact_sizing()
     need = b.output_bytes
+    spare = 16 << 20   # room for crafted streams whose blocks inflate past the declared block maximum
     d_src = ctx.alloc(len(src) + 64)
-    d_dst = ctx.alloc(need + 64)
+    d_dst = ctx.alloc(need + spare + 64)
+    b.set_output_capacity(need + spare)
     try:
         b.upload(d_src)
         b.run(d_src, d_dst)

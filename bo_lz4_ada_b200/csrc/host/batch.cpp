@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <memory>
+#include <mutex>
 
 #include "common.hpp"
 
@@ -52,6 +53,8 @@ struct ItemPlan {
 	Raised host_error;
 	int eof = LZ4ADA_EOF_NO;
 	bool slow = false;
+	bool overflowed = false;   // a block outgrew the frame's block maximum (the reference only bounds it by its Buffer)
+	int min_buffer = 0;        // Min_Buffer_Size of the Init call the stream is decoded under (lib/lz4ada.adb:54, :119)
 	// outcome of the last run
 	Raised error;
 	uint64_t out_len = 0;
@@ -137,15 +140,20 @@ struct lz4ada_batch {
 	int64_t heavy_blocks = -1;                       // blocks that take long to decode (K1 kernel choice), -1 = not counted yet
 	const char *k1_name = "";                        // the K1 kernel the last lz4ada_batch_run launched
 	std::vector<uint32_t> presize;                   // blocks K5 sizes before placement
+	std::vector<uint32_t> presize_max;               // block maximum of the frame each of them belongs to
 	std::vector<uint32_t> sized;                     // their sizes once K5 has run
 	bool have_sized = false;
 	uint64_t out_bytes = 0;
+	uint64_t dst_capacity = 0;   // what the caller's output buffer really holds (lz4ada_batch_set_output_capacity), 0 = out_bytes
+	uint64_t spill_cursor = 0;   // streams that outgrow their region are decoded again behind out_bytes
 	bool placed = false;
 	bool tables_uploaded = false;
 	// device tables
 	lz4b200_blk_desc *d_desc = nullptr;
 	lz4b200_blk_status *d_status = nullptr;
-	lz4b200_chain *d_chains = nullptr;
+	lz4b200_chain *d_chains = nullptr;         // the plan's chains (linked frames), uploaded once
+	lz4b200_chain *d_retry_chains = nullptr;   // chains of the streams a run decodes again (run_slow_items)
+	size_t cap_retry_chains = 0;
 	lz4b200_frame_blocks *d_hash_frames = nullptr;
 	uint32_t *d_digest = nullptr;   // [n_hash] digests then [n_hash] valid flags
 	size_t cap_chains = 0;
@@ -165,12 +173,14 @@ struct lz4ada_batch {
 		if (d_desc) lz4b200_free(ctx, d_desc);
 		if (d_status) lz4b200_free(ctx, d_status);
 		if (d_chains) lz4b200_free(ctx, d_chains);
+		if (d_retry_chains) lz4b200_free(ctx, d_retry_chains);
 		if (d_hash_frames) lz4b200_free(ctx, d_hash_frames);
 		if (d_digest) lz4b200_free(ctx, d_digest);
 		if (h_status) lz4b200_free_host(ctx, h_status);
 		if (h_digest) lz4b200_free_host(ctx, h_digest);
 		for (void *e : ev)
 			if (e) lz4b200_event_destroy(ctx, e);
+		lz4b200_destroy(ctx);   // the batch's reference
 	}
 };
 
@@ -232,7 +242,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 				else run_known = false;
 				const uint64_t hist = off_i;
 				d.hist_avail = hist > 0xfffffffeull ? 0xffffffffu : uint32_t(hist);
-				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
+				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO | LZ4B200_BLK_RING_CAP);
 				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
 				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max) {
@@ -275,7 +285,8 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 		if (!it.user_placed) cursor = it.dst_off + it.dst_cap;
 		else cursor = std::max(cursor, item_end);
 	}
-	b->out_bytes = cursor;
+	b->out_bytes = std::max(b->out_bytes, cursor);   // never shrinks: callers allocate from the first answer
+	b->spill_cursor = b->out_bytes;
 	b->placed = true;
 }
 
@@ -293,6 +304,7 @@ template <class DigestFn>
 bool fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 {
 	if (!exact && it.slow) return true;   // placement already known to be unusable (tight caller buffer)
+	if (!exact) it.overflowed = false;
 	it.error = Raised();
 	it.out_len = 0;
 	bool slow = false;
@@ -303,23 +315,40 @@ bool fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 		else if (fp.dst_off != pos) { slow = true; break; }
 		uint64_t fpos = 0;
 		uint64_t remaining = fp.csize;
+		uint32_t ring = 0;   // the reference's Output_Pos (exact runs bound a block by the caller's Buffer, RING_CAP)
 		for (uint32_t i = 0; i < fp.n_blocks; i++) {
 			const uint32_t bi = fp.first_block + i;
 			const lz4b200_blk_status &st = b->h_status[bi];
 			const lz4b200_blk_desc &d = b->descs[bi];
-			if (st.code == LZ4B200_ST_NEEDS_HISTORY || st.code == LZ4B200_ST_NOT_RUN) { slow = true; break; }
+			if (ring >= uint32_t(kHistorySize)) ring = 0;
+			if (st.code == LZ4B200_ST_NEEDS_HISTORY || st.code == LZ4B200_ST_NOT_RUN || st.code == 0xffffffffu) { slow = true; break; }
 			if (!exact && !fp.chained && d.dst_off != fp.dst_off + fpos) { slow = true; break; }
 			if (fp.has_csize && st.code != LZ4B200_ST_BLOCK_CHECKSUM) {
 				const uint64_t produced = st.code == LZ4B200_ST_OK ? st.out_len : st.err_pos;
 				if (remaining < produced) { it.error = err_content_size_exceeded(); break; }
 			}
 			if (st.code != LZ4B200_ST_OK) {
-				if (st.code == LZ4B200_ST_OUTPUT_OVERFLOW && !exact && d.dst_cap < fp.block_max) { slow = true; break; }
-				it.error = status_to_raised(st, int(std::min<uint64_t>(d.dst_cap, 0x7fffffff)));
+				if (st.code == LZ4B200_ST_OUTPUT_OVERFLOW && !exact) {
+					// The slot (one block maximum, or less in a tight region) was a placement assumption: the reference
+					// bounds a block's output only by the caller's Buffer (lib/lz4ada.adb:54, 813-820).  Decode the
+					// stream again as a chain under that bound.
+					it.overflowed = true;
+					slow = true;
+					break;
+				}
+				int shown = int(std::min<uint64_t>(d.dst_cap, 0x7fffffff));
+				if (st.code == LZ4B200_ST_OUTPUT_OVERFLOW && (d.flags & LZ4B200_BLK_RING_CAP)) {
+					// which bound was hit: the Buffer of the reference's caller, or the room this stream has in the batch output
+					const uint64_t room = it.dst_off + it.dst_cap - (pos + fpos);
+					const uint64_t by_ring = uint64_t(it.min_buffer) > ring ? uint64_t(it.min_buffer) - ring : 0;
+					shown = by_ring <= room ? it.min_buffer : int(std::min<uint64_t>(it.dst_cap, 0x7fffffff));
+				}
+				it.error = status_to_raised(st, shown);
 				break;
 			}
 			remaining -= st.out_len;
 			fpos += st.out_len;
+			ring += st.out_len;
 		}
 		// the reference hands out every block before the failing one (one block per Update)
 		pos += fpos;
@@ -337,9 +366,48 @@ bool fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 	return false;
 }
 
-// Decode the flagged streams again, each as one chain with exact running placement.
+// Streams whose blocks outgrew their slots: size every block with K5 and, where the stream no longer fits the
+// region the plan gave it, move it behind the planned output (as far as the caller's buffer reaches).
+Raised make_room(lz4ada_batch *b, const uint8_t *src_dev)
+{
+	uint32_t lo = 0xffffffffu, hi = 0;
+	for (const ItemPlan &it : b->items)
+		if (it.slow && it.overflowed && it.n_blocks && !it.user_placed) {
+			lo = std::min(lo, it.first_block);
+			hi = std::max(hi, it.first_block + it.n_blocks);
+		}
+	if (lo >= hi) return ok();
+	// (one launch over the block range that spans them: K5 reads the compressed bytes only, a thread per block)
+	const uint32_t n = hi - lo;
+	lz4b200_blk_status *d_ps = nullptr;
+	std::vector<lz4b200_blk_status> ps(n);
+	if (lz4b200_alloc(b->ctx, sizeof(lz4b200_blk_status) * n, reinterpret_cast<void **>(&d_ps)) != LZ4B200_OK) return device_fail(b);
+	const bool bad = lz4b200_size_blocks(b->ctx, src_dev, n, b->d_desc + lo, d_ps) != LZ4B200_OK ||
+			 lz4b200_d2h(b->ctx, ps.data(), d_ps, sizeof(lz4b200_blk_status) * n) != LZ4B200_OK ||
+			 lz4b200_sync(b->ctx) != LZ4B200_OK;
+	lz4b200_free(b->ctx, d_ps);
+	if (bad) return device_fail(b);
+	const uint64_t capacity = std::max(b->dst_capacity, b->out_bytes);
+	for (ItemPlan &it : b->items) {
+		if (!(it.slow && it.overflowed && it.n_blocks && !it.user_placed)) continue;
+		uint64_t total = 0;
+		for (uint32_t i = 0; i < it.n_blocks; i++) total += ps[it.first_block + i - lo].out_len;   // up to the first error, if any
+		if (total <= it.dst_cap) continue;
+		const uint64_t at = align_up(b->spill_cursor, 256);
+		if (at + total > capacity) continue;   // no room: the chain reports the overflow against the region it has
+		it.dst_off = at;
+		it.dst_cap = total;
+		b->spill_cursor = at + total;
+	}
+	return ok();
+}
+
+// Decode the flagged streams again, each as one chain with exact running placement.  In a chain a block is
+// bounded the way the reference bounds it -- by what is left of the caller's Buffer behind the ring cursor
+// (LZ4B200_BLK_RING_CAP), not by the frame's block maximum.
 Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 {
+	if (Raised r = make_room(b, src_dev)) return r;
 	std::vector<lz4b200_chain> chains;
 	for (ItemPlan &it : b->items) {
 		if (!it.slow || it.n_blocks == 0) continue;
@@ -348,9 +416,9 @@ Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
 				d.flags &= ~(LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
-				d.flags |= LZ4B200_BLK_CHAINED;
+				d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_RING_CAP;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
-				d.dst_cap = fp.block_max;
+				d.dst_cap = uint32_t(it.min_buffer);
 			}
 		}
 		lz4b200_chain c;
@@ -364,15 +432,17 @@ Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			return device_fail(b);
 	}
 	if (chains.empty()) return ok();
-	if (chains.size() > b->cap_chains) {
-		if (b->d_chains) lz4b200_free(b->ctx, b->d_chains);
-		b->d_chains = nullptr;
-		b->cap_chains = chains.size();
-		if (lz4b200_alloc(b->ctx, sizeof(lz4b200_chain) * b->cap_chains, reinterpret_cast<void **>(&b->d_chains)) != LZ4B200_OK)
+	// (a buffer of their own: b->d_chains keeps the plan's chains for the next run)
+	if (chains.size() > b->cap_retry_chains) {
+		if (b->d_retry_chains) lz4b200_free(b->ctx, b->d_retry_chains);
+		b->d_retry_chains = nullptr;
+		b->cap_retry_chains = 0;
+		if (lz4b200_alloc(b->ctx, sizeof(lz4b200_chain) * chains.size(), reinterpret_cast<void **>(&b->d_retry_chains)) != LZ4B200_OK)
 			return device_fail(b);
+		b->cap_retry_chains = chains.size();
 	}
-	if (lz4b200_h2d(b->ctx, b->d_chains, chains.data(), sizeof(lz4b200_chain) * chains.size()) != LZ4B200_OK ||
-	    lz4b200_decode_linked(b->ctx, src_dev, dst_dev, uint32_t(chains.size()), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK ||
+	if (lz4b200_h2d(b->ctx, b->d_retry_chains, chains.data(), sizeof(lz4b200_chain) * chains.size()) != LZ4B200_OK ||
+	    lz4b200_decode_linked(b->ctx, src_dev, dst_dev, uint32_t(chains.size()), b->d_retry_chains, b->d_desc, b->d_status) != LZ4B200_OK ||
 	    lz4b200_d2h(b->ctx, b->h_status, b->d_status, sizeof(lz4b200_blk_status) * b->descs.size()) != LZ4B200_OK ||
 	    lz4b200_sync(b->ctx) != LZ4B200_OK)
 		return device_fail(b);
@@ -438,18 +508,24 @@ extern "C" {
 int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes, uint32_t n_items,
 		      const lz4ada_batch_item *items, int reservation, lz4ada_batch **out)
 {
-	if (!out || (!items && n_items) || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SZ_8_MIB)
+	if (!out || (!items && n_items) || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SINGLE_FRAME)
 		return LZ4ADA_ASSERTION_ERROR;
 	*out = nullptr;
 	// planning is pure host work; the device context is only needed from upload on
 	std::unique_ptr<lz4ada_batch> b(new lz4ada_batch());
+	if (ctx) lz4b200_retain(ctx);
 	b->ctx = ctx;
 	b->reservation = reservation;
 	b->src_bytes = src_bytes;
 	b->items.resize(n_items);
-	const int in_last = block_size_of(reservation) + 4 + kBlockSizeBytes - 1;   // as Init, lib/lz4ada.adb:60
+	// A fixed reservation = Init (lib/lz4ada.adb:48-63); Use_First / Single_Frame = Init_With_Header on the whole
+	// stream (:79-125), the call the reference's unlz4ada and its error-case test make
+	const bool with_header = reservation > LZ4ADA_SZ_8_MIB;
+	const int in_last = with_header ? 0 : block_size_of(reservation) + 4 + kBlockSizeBytes - 1;   // as Init, :60
 	for (uint32_t k = 0; k < n_items; k++)
-		if (items[k].src_off > src_bytes || items[k].src_len > src_bytes - items[k].src_off) return LZ4ADA_ASSERTION_ERROR;
+		if (items[k].src_off > src_bytes || items[k].src_len > src_bytes - items[k].src_off ||
+		    items[k].dst_off + items[k].dst_cap < items[k].dst_off)   // a caller-placed region may not wrap
+			return LZ4ADA_ASSERTION_ERROR;
 	// Streams are independent: walk them on a few host threads (the walk touches one size word per block, spread
 	// over the whole compressed buffer -- 10 ms for 4096 frames / 65536 blocks on one thread), each thread into its
 	// own frame / block tables, which are then appended in stream order.
@@ -477,11 +553,28 @@ int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_by
 			it.first_block = uint32_t(pt.descs.size());
 			Meta m;
 			m.reservation = reservation;
-			Walker w(m, in_last, &engine);
-			engine.item = &it;
-			engine.cur = -1;
 			const uint8_t *s = src_host + it.src_off;
 			uint64_t pos = 0;
+			int in_last_k = in_last;
+			it.min_buffer = with_header ? 0 : block_size_of(reservation) + kHistorySize + 8;   // :54
+			if (with_header) {
+				if (it.src_len < 7) {   // Pre => Input'Length >= 7, lib/lz4ada.ads:243
+					it.host_error = err_assertion("failed precondition from lz4ada.ads:243");
+					continue;
+				}
+				int consumed = 0;
+				Raised r = init_with_header_meta(s, int(std::min<uint64_t>(it.src_len, 0x40000000ull)), reservation, m, consumed,
+								 in_last_k, it.min_buffer);
+				if (r) {
+					it.host_error = r;
+					continue;
+				}
+				pos = uint64_t(consumed);
+			}
+			Walker w(m, in_last_k, &engine);
+			engine.item = &it;
+			engine.cur = -1;
+			if (with_header) engine.frame_started(w);   // the first header was consumed by the Init call
 			int idle = 0;
 			while (pos < it.src_len) {
 				const uint64_t left = it.src_len - pos;
@@ -527,7 +620,10 @@ int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_by
 	for (ItemPlan &it : b->items)
 		for (uint32_t f = 0; f + 1 < it.n_frames; f++) {
 			const FramePlan &fp = b->frames[it.first_frame + f];
-			if (fp.n_blocks) b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+			if (fp.n_blocks) {
+				b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+				b->presize_max.push_back(fp.block_max);
+			}
 		}
 	if (b->presize.empty()) place(b.get(), nullptr);
 	else {
@@ -574,20 +670,34 @@ void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read, uint
 	if (checksum_reread) *checksum_reread = b ? b->t_reread : 0;
 }
 
+int lz4ada_batch_set_output_capacity(lz4ada_batch *b, uint64_t bytes)
+{
+	if (!b) return LZ4ADA_ASSERTION_ERROR;
+	b->dst_capacity = bytes;
+	return LZ4ADA_OK;
+}
+
 int lz4ada_batch_exact_sizing(lz4ada_batch *b)
 {
 	if (!b || b->tables_uploaded) return LZ4ADA_ASSERTION_ERROR;
 	b->exact_sizing = true;
 	b->presize.clear();
+	b->presize_max.clear();
 	for (const FramePlan &fp : b->frames) {
 		if (!(fp.independent || fp.n_blocks <= 1)) continue;   // linked frames are chains: placed exactly as they run
-		for (uint32_t i = 0; i < fp.n_blocks; i++) b->presize.push_back(fp.first_block + i);
+		for (uint32_t i = 0; i < fp.n_blocks; i++) {
+			b->presize.push_back(fp.first_block + i);
+			b->presize_max.push_back(fp.block_max);
+		}
 	}
 	// the last block of a linked frame that is followed by another frame still decides that frame's base
 	for (const ItemPlan &it : b->items)
 		for (uint32_t f = 0; f + 1 < it.n_frames; f++) {
 			const FramePlan &fp = b->frames[it.first_frame + f];
-			if (!(fp.independent || fp.n_blocks <= 1) && fp.n_blocks) b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+			if (!(fp.independent || fp.n_blocks <= 1) && fp.n_blocks) {
+				b->presize.push_back(fp.first_block + fp.n_blocks - 1);
+				b->presize_max.push_back(fp.block_max);
+			}
 		}
 	if (!b->presize.empty()) b->placed = false;
 	return LZ4ADA_OK;
@@ -616,7 +726,7 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 	if (!b) return LZ4ADA_ASSERTION_ERROR;
 	if (!b->ctx) {
 		Raised why;
-		b->ctx = default_context(&why);
+		b->ctx = default_context(&why);   // comes with the batch's reference
 		if (!b->ctx) return LZ4ADA_DEVICE_ERROR;
 	}
 	lz4b200_ctx *ctx = b->ctx;
@@ -630,6 +740,7 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 	}
 	if (!b->placed && nb) {
 		// K5 over the blocks that decide frame bases (needs the compressed bytes on the device)
+		if (!src_dev) return LZ4ADA_ASSERTION_ERROR;
 		std::vector<lz4b200_blk_desc> pd(b->presize.size());
 		for (size_t i = 0; i < pd.size(); i++) pd[i] = b->descs[b->presize[i]];
 		lz4b200_blk_desc *d_pd = nullptr;
@@ -649,10 +760,7 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 		sized.assign(pd.size(), 0);
 		b->have_sized = true;
 		for (size_t i = 0; i < pd.size(); i++) {
-			const FramePlan *owner = nullptr;
-			for (const FramePlan &fp : b->frames)
-				if (fp.n_blocks && fp.first_block + fp.n_blocks - 1 == b->presize[i]) { owner = &fp; break; }
-			const uint32_t bm = owner ? owner->block_max : 0xffffffffu;
+			const uint32_t bm = b->presize_max[i];   // the owning frame's block maximum, recorded at plan time
 			// a block K5 cannot walk to its end keeps its block-maximum slot: K1 reports what is wrong with it
 			sized[i] = ps[i].code == LZ4B200_ST_OK ? std::min(ps[i].out_len, bm) : (b->exact_sizing ? 0xffffffffu : std::min(ps[i].out_len, bm));
 		}
@@ -702,6 +810,9 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 		}
 		for (void *&e : b->ev)
 			if (!e && lz4b200_event_create(ctx, &e) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+		// every block's status starts out as "not run" (code 0xffffffff): a block no kernel of this run reached can
+		// never be taken for decoded on the strength of an earlier run's status
+		if (lz4b200_memset(ctx, b->d_status, 0xff, sizeof(lz4b200_blk_status) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		lz4b200_event_record(ctx, b->ev[0]);
 		{
 			// K1's own rule picks the lane-per-block kernel (v5) from the block count alone.  What fills its 75 776
@@ -810,6 +921,8 @@ int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t
 		bool bad = lz4b200_use_lane(ctx, int(c % 3) + 1) != LZ4B200_OK;
 		bad = bad || lz4b200_h2d(ctx, src_dev + s_lo, src_host + s_lo, s_hi - s_lo) != LZ4B200_OK;
 		if (b1 > b0)
+			bad = bad || lz4b200_memset(ctx, b->d_status + b0, 0xff, sizeof(lz4b200_blk_status) * (b1 - b0)) != LZ4B200_OK;
+		if (b1 > b0)
 			bad = bad || lz4b200_decode_blocks(ctx, src_dev, dst_dev, b1 - b0, b->d_desc + b0, b->d_status + b0) != LZ4B200_OK;
 		// chains and frame tables index blocks globally, so they get the un-offset arrays
 		if (ncc)
@@ -846,6 +959,10 @@ int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t
 				return LZ4ADA_DEVICE_ERROR;
 		if (lz4b200_sync(ctx) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 	}
+	// The chunk copies brought back each stream's whole region (its size is only known after the fold): what lies
+	// behind the bytes a stream produced is scratch of earlier calls, not output -- hand back zeros instead.
+	for (const ItemPlan &it : b->items)
+		if (it.n_blocks && it.dst_cap > it.out_len) memset(dst_host + it.dst_off + it.out_len, 0, it.dst_cap - it.out_len);
 	return LZ4ADA_OK;
 }
 
@@ -873,9 +990,11 @@ const char *lz4ada_batch_message(const lz4ada_batch *b, uint32_t item)
 void lz4ada_batch_free(lz4ada_batch *b) { delete b; }
 
 // Device scratch of lz4ada_batch_decompress, kept between calls (cudaMalloc of several GB per call
-// would dominate); one pool per context, freed with the process.
+// would dominate).  The pool belongs to its context (attached to it, shim.cu) and is freed when the
+// context is torn down; the mutex serialises callers that share a context.
 struct ScratchPool {
 	lz4b200_ctx *ctx = nullptr;
+	std::mutex busy;
 	uint8_t *d_src = nullptr, *d_dst = nullptr;
 	uint64_t cap_src = 0, cap_dst = 0;
 	// table buffers handed to (and taken back from) the batch of the current call
@@ -886,19 +1005,29 @@ struct ScratchPool {
 	uint32_t *d_digest = nullptr, *h_digest = nullptr;
 	size_t cap_hash = 0;
 };
-static ScratchPool g_pool[8];
 
-static ScratchPool *pool_for(lz4b200_ctx *ctx)
+static void *pool_make(lz4b200_ctx *ctx)
 {
-	for (ScratchPool &p : g_pool)
-		if (p.ctx == ctx) return &p;
-	for (ScratchPool &p : g_pool)
-		if (!p.ctx) {
-			p.ctx = ctx;
-			return &p;
-		}
-	return nullptr;
+	ScratchPool *p = new (std::nothrow) ScratchPool();
+	if (p) p->ctx = ctx;   // no reference: the context owns the pool, not the other way round
+	return p;
 }
+
+static void pool_free(lz4b200_ctx *ctx, void *obj)
+{
+	ScratchPool *p = static_cast<ScratchPool *>(obj);
+	if (p->d_src) lz4b200_free(ctx, p->d_src);
+	if (p->d_dst) lz4b200_free(ctx, p->d_dst);
+	if (p->d_desc) lz4b200_free(ctx, p->d_desc);
+	if (p->d_status) lz4b200_free(ctx, p->d_status);
+	if (p->h_status) lz4b200_free_host(ctx, p->h_status);
+	if (p->d_hash_frames) lz4b200_free(ctx, p->d_hash_frames);
+	if (p->d_digest) lz4b200_free(ctx, p->d_digest);
+	if (p->h_digest) lz4b200_free_host(ctx, p->h_digest);
+	delete p;
+}
+
+static ScratchPool *pool_for(lz4b200_ctx *ctx) { return static_cast<ScratchPool *>(ctx_attachment(ctx, pool_make, pool_free)); }
 
 static bool pool_reserve(ScratchPool *p, uint64_t src_bytes, uint64_t dst_bytes)
 {
@@ -929,15 +1058,19 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 	std::unique_ptr<lz4ada_batch> guard(b);
 	if (!b->ctx) {
 		Raised why;
-		b->ctx = default_context(&why);
+		b->ctx = default_context(&why);   // comes with the batch's reference
 		if (!b->ctx) return LZ4ADA_DEVICE_ERROR;
 	}
 	ctx = b->ctx;
 	ScratchPool *pool = pool_for(ctx);
 	if (!pool) return LZ4ADA_DEVICE_ERROR;
+	std::lock_guard<std::mutex> pool_lock(pool->busy);
 	const uint64_t need = lz4ada_batch_output_bytes(b);
 	if (need > dst_bytes) return LZ4ADA_ASSERTION_ERROR;
-	if (!pool_reserve(pool, src_bytes, need)) return LZ4ADA_DEVICE_ERROR;
+	// spare room of the caller's buffer (up to 32 MiB of it) serves streams that outgrow their region
+	const uint64_t capacity = need + std::min<uint64_t>(dst_bytes - need, 32ull << 20);
+	b->dst_capacity = capacity;
+	if (!pool_reserve(pool, src_bytes, capacity)) return LZ4ADA_DEVICE_ERROR;
 	uint8_t *d_src = pool->d_src, *d_dst = pool->d_dst;
 	// lend pooled table buffers to the batch when they are large enough (cudaMalloc / cudaMallocHost
 	// per call cost ~100 ms, several times the device stage)

@@ -108,6 +108,11 @@ struct Meta {   // Decompressor_Meta, lib/lz4ada.ads:359-370
 Raised header_feed(Meta &m, uint8_t *header_buffer, const uint8_t *input, int input_len, int &consumed);
 Raised header_magic(Meta &m, uint32_t magic);   // Process_Header_Magic, :199-223
 
+// Init_With_Header (lib/lz4ada.adb:79-125) up to the point where the Decompressor record is built: the
+// first frame header parsed into `mt`, In_Last and Min_Buffer_Size as the reference computes them.
+Raised init_with_header_meta(const uint8_t *input, int input_len, int reservation, Meta &mt, int &num_consumed,
+			     int &in_last, int &min_buffer_size);
+
 class Walker;
 
 struct BlockEngine {
@@ -160,7 +165,11 @@ private:
 	Raised header_bytes(const uint8_t *input, int input_len, int &consumed);
 };
 
-// process-wide default device context (lz4ada_set_device_context)
+// process-wide default device context (lz4ada_set_device_context).  Returned with a reference taken
+// for the caller (drop it with lz4b200_destroy).
 lz4b200_ctx *default_context(Raised *why);
+
+// One host-layer object attached to a device context and freed with it (shim.cu): made on first use.
+void *ctx_attachment(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free_fn)(lz4b200_ctx *, void *));
 
 }  // namespace lz4ada

@@ -23,9 +23,11 @@
 namespace lz4ada {
 
 // ---- process-wide default device context -------------------------------------------------
+// The slot holds one reference of its own on whatever context it names (lz4b200_retain), so a caller who
+// destroys the context it registered -- or replaces the default while decompressors are alive -- leaves
+// nothing dangling: every user of the slot leaves with a reference too.
 static std::mutex g_ctx_mutex;
 static lz4b200_ctx *g_ctx = nullptr;
-static bool g_ctx_owned = false;
 
 lz4b200_ctx *default_context(Raised *why)
 {
@@ -38,9 +40,9 @@ lz4b200_ctx *default_context(Raised *why)
 						  "decode path");
 			return nullptr;
 		}
-		g_ctx = c;
-		g_ctx_owned = true;
+		g_ctx = c;   // the creator's reference becomes the slot's
 	}
+	lz4b200_retain(g_ctx);
 	return g_ctx;
 }
 
@@ -58,6 +60,7 @@ public:
 			if (h_stage_) lz4b200_free_host(ctx_, h_stage_);
 		}
 		if (stream_) lz4b200_stream_destroy(stream_);
+		if (ctx_) lz4b200_destroy(ctx_);   // the engine's reference (default_context took it)
 	}
 
 	Raised new_frame(Walker &) override   // Reset_Outer_For_Next_Frame, lib/lz4ada.adb:451-461
@@ -260,9 +263,12 @@ private:
 	{
 		if (stream_) return ok();
 		Raised why;
-		ctx_ = default_context(&why);
+		if (!ctx_) ctx_ = default_context(&why);
 		if (!ctx_) return why;
-		if (lz4b200_stream_create(ctx_, max_block_, &stream_) != LZ4B200_OK) return device_failure();
+		if (lz4b200_stream_create(ctx_, max_block_, &stream_) != LZ4B200_OK) {
+			stream_ = nullptr;
+			return device_failure();
+		}
 		return ok();
 	}
 	Raised device_failure() { return err_device(ctx_ ? lz4b200_last_error(ctx_) : "no device context"); }
@@ -300,9 +306,10 @@ extern "C" {
 int lz4ada_set_device_context(lz4b200_ctx *ctx)
 {
 	std::lock_guard<std::mutex> lock(g_ctx_mutex);
-	if (g_ctx && g_ctx_owned && g_ctx != ctx) lz4b200_destroy(g_ctx);
+	if (g_ctx == ctx) return LZ4ADA_OK;
+	if (ctx) lz4b200_retain(ctx);
+	if (g_ctx) lz4b200_destroy(g_ctx);   // the slot's reference; live decompressors hold their own
 	g_ctx = ctx;
-	g_ctx_owned = false;
 	return LZ4ADA_OK;
 }
 
@@ -330,29 +337,13 @@ int lz4ada_init_with_header(const uint8_t *input, int input_len, int *num_consum
 		copy_message(message, message_cap, r.text);
 		return r.kind;
 	}
-	uint8_t header_buffer[20];
 	Meta mt;
-	mt.reservation = reservation == LZ4ADA_SINGLE_FRAME ? LZ4ADA_USE_FIRST : reservation;
-	int pos = 0;
-	while (mt.stage != HeaderStage::Complete) {
-		if (pos >= input_len) {
-			r = err_too_few_header_bytes(mt.size_remaining);
-			copy_message(message, message_cap, r.text);
-			return r.kind;
-		}
-		int inner = 0;
-		r = header_feed(mt, header_buffer, input + pos, input_len - pos, inner);
-		if (r) {
-			copy_message(message, message_cap, r.text);
-			return r.kind;
-		}
-		pos += inner;
-		*num_consumed += inner;
+	int in_last = 0;
+	r = init_with_header_meta(input, input_len, reservation, mt, *num_consumed, in_last, *min_buffer_size);
+	if (r) {
+		copy_message(message, message_cap, r.text);
+		return r.kind;
 	}
-	const int block_max = block_size_of(mt.reservation);
-	const int in_last = block_max + mt.block_checksum_length + kBlockSizeBytes - 1;
-	*min_buffer_size = block_max + kHistorySize + 8;
-	if (reservation == LZ4ADA_SINGLE_FRAME) mt.reservation = LZ4ADA_SINGLE_FRAME;
 	*out = new lz4ada_decompressor(mt, in_last, *min_buffer_size);
 	return LZ4ADA_OK;
 }
@@ -363,6 +354,9 @@ int lz4ada_init_for_block(int *min_buffer_size, int compressed_length, int reser
 	if (!min_buffer_size || !out || reservation < LZ4ADA_SZ_64_KIB || reservation > LZ4ADA_SZ_8_MIB)
 		return LZ4ADA_ASSERTION_ERROR;
 	const int block_max = block_size_of(reservation);
+	// Input_Buffer is (0 .. Block_Max_Size - 1): a longer block cannot be cached (the reference dies with
+	// Constraint_Error inside Cache_Data_And_Process_If_Full, lib/lz4ada.adb:646); a negative length is no length
+	if (compressed_length < 0 || compressed_length > block_max) return LZ4ADA_ASSERTION_ERROR;
 	*min_buffer_size = block_max + kHistorySize + 8;
 	Meta m;
 	m.format = Format::Block;

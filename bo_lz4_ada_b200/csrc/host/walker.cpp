@@ -124,6 +124,29 @@ Raised header_feed(Meta &m, uint8_t *hb, const uint8_t *input, int input_len, in
 	}
 }
 
+// Init_With_Header, lib/lz4ada.adb:79-125: feed header bytes until the first header is complete.
+Raised init_with_header_meta(const uint8_t *input, int input_len, int reservation, Meta &mt, int &num_consumed,
+			     int &in_last, int &min_buffer_size)
+{
+	num_consumed = 0;
+	uint8_t header_buffer[20];
+	mt = Meta();
+	mt.reservation = reservation == LZ4ADA_SINGLE_FRAME ? LZ4ADA_USE_FIRST : reservation;
+	int pos = 0;
+	while (mt.stage != HeaderStage::Complete) {
+		if (pos >= input_len) return err_too_few_header_bytes(mt.size_remaining);   // :104
+		int inner = 0;
+		if (Raised r = header_feed(mt, header_buffer, input + pos, input_len - pos, inner)) return r;
+		pos += inner;
+		num_consumed += inner;
+	}
+	const int block_max = block_size_of(mt.reservation);
+	in_last = block_max + mt.block_checksum_length + kBlockSizeBytes - 1;   // :117-118
+	min_buffer_size = block_max + kHistorySize + 8;                          // :119
+	if (reservation == LZ4ADA_SINGLE_FRAME) mt.reservation = LZ4ADA_SINGLE_FRAME;
+	return ok();
+}
+
 // ------------------------------------------------------------------------------------------
 
 Walker::Walker(const Meta &meta, int in_last, BlockEngine *eng)

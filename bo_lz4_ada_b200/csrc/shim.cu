@@ -2,9 +2,11 @@
 // kernel launches K1..K5.  Compiled by nvcc for sm_100a only; everything exported is extern "C".
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "kernels.cuh"
@@ -105,6 +107,16 @@ decode_blocks_v5_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 	v5::decode_lanes(src, dst, n_blocks, desc, status, counter, wms[warp], lane);
 }
 
+// LZ4B200_BLK_RING_CAP: the block's dst_cap is the length of the reference caller's Buffer; what the block may
+// produce is what is left of that Buffer behind the ring cursor (lib/lz4ada.adb:678-680: the cursor goes back to 0
+// at a block start once it has passed the 64 KiB history).  `ring` = cursor before this block, updated in place.
+__device__ __forceinline__ uint32_t ring_block_cap(const lz4b200_blk_desc &d, uint32_t &ring)
+{
+	if (!(d.flags & LZ4B200_BLK_RING_CAP)) return d.dst_cap;
+	if (ring >= 65536u) ring = 0;
+	return d.dst_cap > ring ? d.dst_cap - ring : 0u;
+}
+
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
 // simply reads backwards across block boundaries of its frame.
 __global__ void __launch_bounds__(K1_WARPS * 32)
@@ -121,6 +133,7 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 	uint8_t *out = dst + ch.dst_off;
 	uint64_t pos = 0;         // chain-relative output position
 	uint64_t frame_start = 0; // chain-relative position where the current frame began
+	uint32_t ring = 0;        // Output_Pos of the reference's Buffer (LZ4B200_BLK_RING_CAP blocks)
 	bool failed = false;
 	for (uint32_t i = 0; i < ch.n_blocks; i++) {
 		const uint32_t b = ch.first_block + i;
@@ -136,11 +149,12 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 			continue;
 		}
 		const lz4b200_blk_desc d = desc[b];
-		if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+		if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
 		const uint64_t fpos = pos - frame_start;
 		const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
 		const uint64_t room = ch.dst_cap - pos;
-		const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+		const uint32_t blk_cap = ring_block_cap(d, ring);
+		const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
 		// fast path (kernels_v2.cuh) when the frame position fits 32 bits and the block is an
 		// ordinary compressed one; the exact routine otherwise and for anything unusual
 		bool fast_done = false;
@@ -176,7 +190,7 @@ decode_linked_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_c
 		const uint32_t code = status[b].code;      // lane 0 wrote it; visible after __syncwarp
 		const uint32_t out_len = status[b].out_len;
 		if (code != LZ4B200_ST_OK) failed = true;
-		else pos += out_len;
+		else { pos += out_len; ring += out_len; }
 	}
 }
 
@@ -228,15 +242,17 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 	if (warp == 0) {
 		// ---------------- parser ----------------
 		uint64_t pos = 0, frame_start = 0;   // chain-relative
+		uint32_t ring = 0;                   // Output_Pos of the reference's Buffer (LZ4B200_BLK_RING_CAP blocks)
 		uint32_t k = 0;                      // batches published
 		bool stop = false;
 		for (uint32_t i = 0; i < ch.n_blocks && !stop; i++) {
 			const uint32_t b = ch.first_block + i;
 			const lz4b200_blk_desc d = desc[b];
-			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
 			const uint64_t fpos0 = pos - frame_start;
 			const uint64_t room = ch.dst_cap - pos;
-			const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+			const uint32_t blk_cap = ring_block_cap(d, ring);
+			const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
 			const uint8_t *s = src + d.src_off;
 			const bool stored = (d.flags & LZ4B200_BLK_STORED) != 0;
 			const bool ordinary = !(d.flags & LZ4B200_BLK_HASH_ONLY) && fpos0 + cap < 0xfff00000ull &&
@@ -436,6 +452,7 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 					status[b].xxh32_declared = declared;
 				}
 				pos += fpos - static_cast<uint32_t>(fpos0);
+				ring += fpos - static_cast<uint32_t>(fpos0);
 			} else {
 				// anything out of the ordinary: drain the pipeline, then the exact routine takes over from this block
 				if (lane == 0 && vload(&ps.fail_block) == 0xffffffffu) atomicMin(&ps.fail_block, i);
@@ -505,13 +522,16 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 	const uint32_t fbk = ps.fail_block;
 	if (fbk != 0xffffffffu && warp == 0) {
 		uint64_t pos = 0, frame_start = 0;
+		uint32_t ring = 0;
 		bool failed = false;
 		for (uint32_t i = 0; i < ch.n_blocks; i++) {
 			const uint32_t b = ch.first_block + i;
 			const lz4b200_blk_desc d = desc[b];
-			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) frame_start = pos;
+			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
 			if (i < fbk) {   // finished by the pipeline
+				ring_block_cap(d, ring);   // (the cursor's wrap at this block's start)
 				pos += status[b].out_len;
+				ring += status[b].out_len;
 				continue;
 			}
 			if (failed) {
@@ -524,7 +544,8 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 			}
 			const uint64_t fpos = pos - frame_start;
 			const uint64_t room = ch.dst_cap - pos;
-			const uint32_t cap = room < d.dst_cap ? static_cast<uint32_t>(room) : d.dst_cap;
+			const uint32_t blk_cap = ring_block_cap(d, ring);
+			const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
 			if (d.flags & LZ4B200_BLK_SOLO) {
 				// a chain of one block taken out of an independent frame: independent semantics
 				process_block<false>(src, out + pos, d, cap, d.hist_avail, status + b, lane);
@@ -534,7 +555,7 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 			}
 			__syncwarp();
 			if (status[b].code != LZ4B200_ST_OK) failed = true;
-			else pos += status[b].out_len;
+			else { pos += status[b].out_len; ring += status[b].out_len; }
 		}
 	}
 }
@@ -768,6 +789,15 @@ size_blocks_kernel(const uint8_t *__restrict__ src, uint32_t n_blocks,
 // ------------------------------------------------------------------------------------------
 
 struct lz4b200_ctx {
+	// Shared ownership: the creator holds one reference (dropped by lz4b200_destroy); every stream object,
+	// decompressor, batch and the default-context slot of the LZ4Ada layer holds one more (lz4b200_retain).
+	// The CUDA objects are torn down when the last reference goes, so a child outliving its creator's
+	// lz4b200_destroy keeps working instead of touching freed memory.
+	std::atomic<int> refs{1};
+	// host-layer scratch kept per context (batch.cpp's pool): freed with the context
+	std::mutex attach_mutex;
+	void *attachment = nullptr;
+	void (*attachment_free)(lz4b200_ctx *, void *) = nullptr;
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;      // the lane in use (lz4b200_use_lane)
@@ -793,6 +823,20 @@ static int fail(lz4b200_ctx *ctx, cudaError_t e, const char *what)
 		cudaError_t e_ = (call);                                                \
 		if (e_ != cudaSuccess) return fail(ctx, e_, #call);                     \
 	} while (0)
+
+// Host-layer attachment (not part of the C-ABI: C++ linkage, see host/common.hpp).
+namespace lz4ada {
+void *ctx_attachment(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free_fn)(lz4b200_ctx *, void *))
+{
+	if (!ctx) return nullptr;
+	std::lock_guard<std::mutex> lock(ctx->attach_mutex);
+	if (!ctx->attachment && make) {
+		ctx->attachment = make(ctx);
+		ctx->attachment_free = free_fn;
+	}
+	return ctx->attachment;
+}
+}  // namespace lz4ada
 
 extern "C" {
 
@@ -850,11 +894,21 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 	return LZ4B200_OK;
 }
 
+int lz4b200_retain(lz4b200_ctx *ctx)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	ctx->refs.fetch_add(1, std::memory_order_relaxed);
+	return LZ4B200_OK;
+}
+
 int lz4b200_destroy(lz4b200_ctx *ctx)
 {
 	if (!ctx) return LZ4B200_OK;
+	if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) > 1) return LZ4B200_OK;   // children still hold it
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->lanes[0]);
+	if (ctx->attachment && ctx->attachment_free) ctx->attachment_free(ctx, ctx->attachment);
+	ctx->attachment = nullptr;
 	if (ctx->d_prof) {
 		static const char *names[v3::PROF_N] = {"load", "parse", "scan", "emit", "match", "flush", "exact", "blocks", "windows",
 							"iters", "fallback", "batches", "rounds", "early", "gatewait", "coop"};
@@ -1224,20 +1278,29 @@ constexpr size_t META_DESC = 0, META_STATUS = 64, META_XXH = 128, META_DIGEST = 
 int lz4b200_stream_create(lz4b200_ctx *ctx, uint32_t max_block, lz4b200_stream **out)
 {
 	if (!ctx || !out) return LZ4B200_ERR_ARG;
+	*out = nullptr;
 	lz4b200_stream *s = new (std::nothrow) lz4b200_stream();
 	if (!s) return LZ4B200_ERR_NOMEM;
 	s->ctx = ctx;
+	lz4b200_retain(ctx);
 	s->max_block = max_block;
 	s->win_size = HISTORY + 2 * static_cast<size_t>(max_block) + 256;
-	CK(cudaSetDevice(ctx->device));
-	CK(cudaMalloc(&s->d_src, static_cast<size_t>(max_block) + 64));
-	CK(cudaMalloc(&s->d_win, s->win_size + 64));
-	CK(cudaMalloc(&s->d_meta, META_BYTES));
-	CK(cudaMallocHost(&s->h_meta, META_BYTES));
-	s->cursor = HISTORY;
-	xxh32_stream_reset_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH));
-	ctx->launches++;
-	CK(cudaGetLastError());
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_src, static_cast<size_t>(max_block) + 64);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_win, s->win_size + 64);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_meta, META_BYTES);
+	if (e == cudaSuccess) e = cudaMallocHost(&s->h_meta, META_BYTES);
+	if (e == cudaSuccess) {
+		s->cursor = HISTORY;
+		xxh32_stream_reset_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH));
+		ctx->launches++;
+		e = cudaGetLastError();
+	}
+	if (e != cudaSuccess) {
+		const int rc = fail(ctx, e, "lz4b200_stream_create");
+		lz4b200_stream_destroy(s);
+		return rc;
+	}
 	*out = s;
 	return LZ4B200_OK;
 }
@@ -1251,6 +1314,7 @@ int lz4b200_stream_destroy(lz4b200_stream *s)
 	cudaFree(s->d_win);
 	cudaFree(s->d_meta);
 	cudaFreeHost(s->h_meta);
+	lz4b200_destroy(s->ctx);   // drops the stream's reference
 	delete s;
 	return LZ4B200_OK;
 }

@@ -66,6 +66,10 @@ typedef struct lz4b200_blk_desc {
 #define LZ4B200_BLK_HASH_ONLY     4u  /* verify checksum, do not decode (used by retries) */
 #define LZ4B200_BLK_CHAINED       8u  /* decoded in order by lz4b200_decode_linked; K1 skips it */
 #define LZ4B200_BLK_FIRST_OF_FRAME 16u /* chain kernel: a new frame starts here, history restarts */
+#define LZ4B200_BLK_RING_CAP      64u /* chain kernel: dst_cap is the length of the reference caller's Buffer
+                                       * (Min_Buffer_Size = reservation block size + 64 KiB + 8, lib/lz4ada.adb:54);
+                                       * the block may produce what is left of it behind the ring cursor
+                                       * (:678-680) -- the only bound the reference puts on a block's output */
 #define LZ4B200_BLK_SOLO          32u /* chain of one block taken from an independent frame (big blocks get a
                                        * whole CTA): its exact path keeps independent-block semantics */
 
@@ -125,6 +129,14 @@ typedef struct lz4b200_hash_span {
  * caller owns (e.g. torch's current stream) or NULL to let the context create
  * its own non-blocking stream.  A context is used by one host thread at a time. */
 int lz4b200_create(int device, void *stream, lz4b200_ctx **out);
+/* A context is reference counted.  lz4b200_create returns it with one reference (the caller's);
+ * lz4b200_destroy drops one, and the CUDA objects go when the last one is dropped.  Every stream
+ * object, decompressor and batch made on a context holds its own reference, so destroying the
+ * context before its children is safe: they keep working and the teardown happens with the last
+ * of them (the shape an Ada Limited_Controlled finaliser needs -- finalisation order of a
+ * Decompressor and its device context is not the caller's to choose).  lz4b200_retain takes an
+ * additional reference for a holder of its own. */
+int lz4b200_retain(lz4b200_ctx *ctx);
 int lz4b200_destroy(lz4b200_ctx *ctx);
 /* Text of the last CUDA failure seen by this context (never NULL). */
 const char *lz4b200_last_error(const lz4b200_ctx *ctx);
@@ -346,7 +358,11 @@ typedef struct lz4ada_batch lz4ada_batch;
 /* Host stage: parse every frame header and walk the block size words
  * (lib/lz4ada.adb:155-361, 525-585) to build the block table.  Needs the
  * compressed bytes in host memory (`src_host`); nothing is decoded here.
- * ctx may be NULL (the process-wide default context is taken at upload). */
+ * ctx may be NULL (the process-wide default context is taken at upload).
+ * reservation: LZ4ADA_SZ_64_KIB .. LZ4ADA_SZ_8_MIB decode every stream as Init(reservation) + Update
+ * would; LZ4ADA_USE_FIRST / LZ4ADA_SINGLE_FRAME as Init_With_Header(stream, reservation) + Update
+ * (lib/lz4ada.adb:79-125; the call tool_unlz4ada and Test_Error_Case make), including
+ * Too_Few_Header_Bytes and the Single_Frame policing. */
 int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_bytes,
 		uint32_t n_items, const lz4ada_batch_item *items, int reservation,
 		lz4ada_batch **out);
@@ -367,6 +383,16 @@ void lz4ada_batch_traffic(const lz4ada_batch *b, uint64_t *compressed_read,
  * launching stream: ms[0] = K1 (independent blocks), ms[1] = K4 (chains), ms[2] = K3 (content
  * checksums).  0 for a kernel that did not run. */
 int lz4ada_batch_kernel_ms(const lz4ada_batch *b, float ms[3]);
+
+/* How many bytes the caller's output buffer (dst_dev) really holds, when that is more than
+ * lz4ada_batch_output_bytes.  The plan gives every block one block maximum of room, which is what every
+ * well-formed frame needs.  The reference, however, bounds a block's output only by its caller's Buffer
+ * (Min_Buffer_Size = reservation + 64 KiB + 8, lib/lz4ada.adb:54, 813-820), so a crafted frame whose block
+ * inflates past the declared block maximum decodes there (test vector cntblkszoverflow under Init(For_All)).
+ * Such a stream is decoded again as a chain under the reference's bound; when it no longer fits its region
+ * it is placed behind the planned output, in [output_bytes, capacity), and its result reports that dst_off.
+ * Without spare capacity it ends with Data_Corruption "Output buffer exhausted ..." naming its region. */
+int lz4ada_batch_set_output_capacity(lz4ada_batch *b, uint64_t bytes);
 
 /* Exact sizing: call between lz4ada_batch_plan and lz4ada_batch_upload.
  * The upload then runs the size pre-pass K5 over every block of the independent-block frames and

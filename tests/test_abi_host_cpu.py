@@ -201,6 +201,46 @@ def test_planner_host_errors_match_oracle_streaming(oracle):
             assert ho["end_of_frame"] == eof, (c, ho, eof)
 
 
+def test_planner_init_with_header_semantics(oracle):
+    """Reservation Single_Frame / Use_First plans every stream as Init_With_Header(stream) + Update
+    (lib/lz4ada.adb:79-125): the host-detectable .err vectors give their .eds line (first 10 001 bytes, like
+    Test_Error_Case), concatenated frames trip the Single_Frame policing, a stream shorter than 7 bytes violates
+    the precondition, and a block table comes out for the good ones -- all without a device."""
+    host_cases = ["corruptedmagic", "z1ver", "corruptedreserved", "corruptedblocksz", "corruptedhdrchck", "t2e",
+                  "cntblkszoverflow"]
+    streams = [_read(c + ".err")[:10001] for c in host_cases]
+    extra = [_read("concatlegacy.lz4"), _read("concat390.lz4"), _read("t300k.lz4"), b"\x04\x22\x4d"]
+    b = lz.Batch(None, b"".join(streams + extra), _offsets(streams + extra), Reservation="Single_Frame")
+    for k, c in enumerate(host_cases):
+        ho = b.host_outcome(k)
+        assert ho["message"] == MAN["error"][c]["eds"], c
+    ho = b.host_outcome(len(host_cases))
+    assert ho["exception"] == "DATA_CORRUPTION" and "looks like the beginning of another frame" in ho["message"]
+    ho = b.host_outcome(len(host_cases) + 1)
+    # modern + modern: the first frame must be decoded before the policing fires (content checksum first), so the
+    # host stage records the error; it is reported unless a device-side error comes earlier in stream order
+    assert ho["exception"] == "DATA_CORRUPTION" and "data was provided after End of Frame" in ho["message"]
+    ho = b.host_outcome(len(host_cases) + 2)
+    assert ho["exception"] == "OK" and ho["n_blocks"] == 5 and ho["end_of_frame"] == "Yes"
+    ho = b.host_outcome(len(host_cases) + 3)
+    assert ho["exception"] == "ASSERTION_ERROR"
+    b.close()
+    # Use_First: no policing, concatenated frames are walked to the end
+    b = lz.Batch(None, b"".join(extra[:2]), _offsets(extra[:2]), Reservation="Use_First")
+    for k in range(2):
+        ho = b.host_outcome(k)
+        assert ho["exception"] == "OK" and ho["n_frames"] == 2, ho
+    b.close()
+
+
+def _offsets(streams):
+    offs, pos = [], 0
+    for s in streams:
+        offs.append((pos, len(s)))
+        pos += len(s)
+    return offs
+
+
 def test_planner_truncated_streams(oracle):
     """Streams cut at every prefix length: the planner never invents an error and reports the same
     Is_End_Of_Frame as the oracle fed the same prefix."""

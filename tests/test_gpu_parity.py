@@ -268,16 +268,170 @@ def test_batch_error_vectors_match_oracle(ctx, oracle):
     res = lz.batch_decompress(ctx, streams)
     for stem, data, (exc, out, eof, msg) in zip(ERR, streams, res):
         oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 22)
-        if stem == "cntblkszoverflow":
-            # Under Init(For_All) the reference accepts this 64 KiB-block frame whose single block
-            # inflates to 100 KiB (it never bounds a block's decompressed size).
-            # The batch path bounds every block by the frame's declared block maximum.
-            assert oexc == "OK" and len(oout) == 102400
-            assert exc == "DATA_CORRUPTION" and "Output buffer exhausted" in msg and out == b""
-            continue
         assert (exc, msg) == (oexc, omsg), stem
         assert out == oout, stem
 
+
+
+def test_batch_block_outgrows_block_max(ctx, oracle):
+    """The reference bounds a block's output by its caller's Buffer only (lib/lz4ada.adb:54, 813-820): under
+    Init(For_All) it accepts cntblkszoverflow.err, a 64 KiB-block frame whose single block inflates to 100 KiB.
+    The batch call decodes such a stream again as a chain under that bound, moved behind the planned output
+    when it outgrows its region; without spare room it ends with the oracle-style Output-buffer text."""
+    data = _read("cntblkszoverflow.err")
+    oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 22)
+    assert oexc == "OK" and len(oout) == 102400
+    text = corpus.text_like(200000, seed=5)
+    good = corpus.build_frame(text, 4, True, True)
+    info = {}
+    res = lz.batch_decompress(ctx, [good, data, good, data], info=info)
+    assert info["retried_streams"] == 2
+    for k, plain in ((0, text), (1, oout), (2, text), (3, oout)):
+        assert res[k][0] == "OK" and res[k][1] == plain, (k, res[k][0], res[k][3])
+    # no spare capacity: the overflow is reported against the region the stream has (one block maximum)
+    b = lz.Batch(ctx, data, [(0, len(data))])
+    d_src, d_dst = ctx.alloc(len(data) + 64), ctx.alloc(b.output_bytes + 64)
+    b.upload(d_src)
+    b.run(d_src, d_dst)
+    r = b.results()[0]
+    assert r["exception"] == "DATA_CORRUPTION" and r["out_len"] == 0
+    assert r["message"] == ("raised LZ4ADA.DATA_CORRUPTION : Output buffer exhausted. Decompressed data does not fit "
+                            "into the 65536 bytes provided.")
+    b.close()
+    ctx.free(d_src)
+    ctx.free(d_dst)
+    # a frame of several blocks, one of which is 30 KiB of compressed zeros-with-noise inflating past 64 KiB:
+    # build it by hand -- a 4 MiB-block payload inside a frame that declares 64 KiB blocks
+    big = corpus.compress_block(bytes(150000) + text[:20000])
+    hdr = corpus.frame_header(4, False, True)
+    frame = hdr + struct.pack("<I", len(big)) + big + struct.pack("<I", 0) + struct.pack("<I", corpus.xxh32(bytes(150000) + text[:20000]))
+    oexc, oout, oeof, omsg = oracle.decode_stream(frame, chunk=0, out_cap=1 << 22)
+    assert oexc == "OK" and oout == bytes(150000) + text[:20000]
+    (exc, out, eof, msg), = lz.batch_decompress(ctx, [frame])
+    assert (exc, out) == (oexc, oout), msg
+
+
+@pytest.mark.parametrize("reservation", ["Single_Frame", "Use_First"])
+def test_batch_error_vectors_init_with_header(ctx, oracle, reservation):
+    """Test_Error_Case (lz4test.adb:280-351) through the batch call: first 10 001 bytes of every .err vector,
+    decoded as Init_With_Header(all, Single_Frame) + Update would -- the message must be the .eds line itself."""
+    streams = [_read(s + ".err")[:10001] for s in ERR] + [_read(s + ".lz4") for s in GOOD]
+    res = lz.batch_decompress(ctx, streams, Reservation=reservation)
+    for stem, data, (exc, out, eof, msg) in zip(ERR, streams, res):
+        if reservation == "Single_Frame":
+            assert msg == MAN["error"][stem]["eds"], stem
+            oexc, oout, omsg = oracle.decode_error_case(data)
+            assert (exc, out) == (oexc, oout), stem
+        elif stem != "trailingbytes":   # the one vector whose error is the Single_Frame policing itself
+            assert msg == MAN["error"][stem]["eds"], stem
+    for stem, data, (exc, out, eof, msg) in zip(GOOD, streams[len(ERR):], res[len(ERR):]):
+        oexc, oout, omsg = _oracle_with_header(oracle, data, reservation)
+        assert (exc, msg, out) == (oexc, omsg, oout), stem
+        if exc == "OK":
+            _check_output(stem, out)
+
+
+def _oracle_with_header(oracle, data, reservation):
+    """Init_With_Header(data, reservation) + Update until the input is used up -> (exception, output, message)."""
+    import oracle_binding
+    out = bytearray()
+    try:
+        o, pos = oracle.init_with_header(data, reservation)
+        while pos < len(data):
+            c, piece, _, _ = o.update(data[pos:])
+            out += piece
+            pos += c
+            assert c > 0 or piece
+    except oracle_binding.OracleError as e:
+        return e.name, bytes(out), e.message
+    return "OK", bytes(out), ""
+
+
+def test_context_lifetime(oracle):
+    """A device context is reference counted: closing it before the objects made on it (the order the driver's
+    smoke() used, and the order an Ada finaliser may pick) must neither crash nor stop them working; a second
+    context made afterwards starts clean (no stale scratch keyed by address)."""
+    import ctypes
+    import gc
+    data = _read("t300k.lz4")
+    plain = _read("t300k.bin")
+    c1 = lz.DeviceContext(0)
+    c1.make_default()
+    dec = lz.Init()
+    c0, o0, _, _ = dec.Update(data[:70000])          # the stream object now exists on c1
+    lz.lib().lz4ada_set_device_context(None)
+    c1.close()                                        # creator's reference gone; dec still holds one
+    got, pos = bytearray(o0), c0
+    while pos < len(data):
+        c, o, _, _ = dec.Update(data[pos:pos + 4096])
+        got += o
+        pos += c
+    assert bytes(got) == plain
+    dec.close()
+    del dec
+    gc.collect()
+    # one-shot calls on contexts that come and go (the scratch pool is owned by its context)
+    text = corpus.text_like(400000, seed=9)
+    frame = corpus.build_frame(text, 4, True, True)
+    for rep in range(12):
+        c = lz.DeviceContext(0)
+        items = (lz.BatchItem * 1)()
+        items[0].src_off, items[0].src_len = 0, len(frame)
+        results = (lz.BatchResult * 1)()
+        out = bytearray(len(text) + (1 << 16))
+        addr = (ctypes.c_uint8 * len(out)).from_buffer(out)
+        rc = lz.lib().lz4ada_batch_decompress(c.handle, frame, len(frame), addr, len(out), 1, items,
+                                              lz.RESERVATIONS["For_All"], results, None, 0)
+        assert rc == 0 and results[0].exception == 0
+        assert bytes(out[results[0].dst_off:results[0].dst_off + results[0].out_len]) == text
+        c.close()
+    # a batch outliving its context
+    c = lz.DeviceContext(0)
+    b = lz.Batch(c, frame, [(0, len(frame))])
+    d_src, d_dst = c.alloc(len(frame) + 64), c.alloc(b.output_bytes + 64)
+    b.upload(d_src)
+    handle = c.handle
+    lz.lib().lz4b200_retain(handle)   # keep our own reference for the device buffers below
+    c.close()
+    b.run(d_src, d_dst)
+    assert b.results()[0]["exception"] == "OK"
+    b.close()
+    c.handle = handle
+    assert c.d2h(d_dst, len(text)) == text
+    c.free(d_src)
+    c.free(d_dst)
+    c.close()
+
+
+def test_batch_run_twice_with_retries_and_chains(ctx):
+    """lz4ada_batch_run is repeatable: a run that had to decode some streams again as chains (short interior
+    blocks) must leave the plan's own chain table (linked frames) intact for the next run -- every run into a
+    cleared output buffer has to produce all the bytes again."""
+    text = corpus.text_like(600000, seed=31)
+    streams = [corpus.build_frame(text[:300000], 4, True, True, independent=False),           # linked: a plan chain
+               corpus.build_frame(text[100000:400000], 4, False, True, block_size=30000),     # short blocks: retried
+               corpus.build_frame(text[200000:], 5, True, True, independent=False),           # linked
+               corpus.build_frame(text[:200000], 4, True, True)]
+    plains = [text[:300000], text[100000:400000], text[200000:], text[:200000]]
+    src = b"".join(streams)
+    offs, pos = [], 0
+    for st in streams:
+        offs.append((pos, len(st)))
+        pos += len(st)
+    b = lz.Batch(ctx, src, offs)
+    need = b.output_bytes
+    d_src, d_dst = ctx.alloc(len(src) + 64), ctx.alloc(need + 64)
+    b.upload(d_src)
+    for rep in range(3):
+        lz.lib().lz4b200_memset(ctx.handle, d_dst, 0xA5 + rep, need)
+        b.run(d_src, d_dst)
+        assert b.retried_streams() == 1
+        for plain, r in zip(plains, b.results()):
+            assert r["exception"] == "OK", (rep, r["message"])
+            assert ctx.d2h(d_dst + r["dst_off"], r["out_len"]) == plain, rep
+    b.close()
+    ctx.free(d_src)
+    ctx.free(d_dst)
 
 
 def test_batch_exact_sizing(ctx, oracle):
