@@ -14,6 +14,7 @@
 #include "kernels_v3.cuh"
 #include "kernels_v4.cuh"
 #include "kernels_v5.cuh"
+#include "kernels_v6.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -116,6 +117,28 @@ __device__ __forceinline__ uint32_t ring_block_cap(const lz4b200_blk_desc &d, ui
 	if (ring >= 65536u) ring = 0;
 	return d.dst_cap > ring ? d.dst_cap - ring : 0u;
 }
+
+// K1 sixth generation (kernels_v6.cuh): a lane per block again, one piece of a sequence (<= 8 literal + <= 16 match bytes) per
+// trip, the parse K pieces ahead of the copy (old match sources requested that far ahead), literals inside the descriptors.
+template <uint32_t OWW, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+decode_blocks_v6_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t *counter, uint32_t hints)
+{
+	// one CTA per SM; the launch picks its number of warps (<= WARPS) from the block count
+	extern __shared__ __align__(16) uint8_t v6_smem[];
+	using L = v6::Layout<OWW, K>;
+	const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(v6_smem));
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t side = s0 + warp * L::SIDE_WARP;
+	const uint32_t in_base = side + lane * v6::IN_STRIDE;
+	const uint32_t stage_base = side + L::IN_WARP + lane * v6::STAGE_SLOT;
+	const uint32_t rings0 = (s0 + WARPS * L::SIDE_WARP + L::OUT_WARP - 1u) & ~(L::OUT_WARP - 1u);
+	const uint32_t ring_base = rings0 + warp * L::OUT_WARP + lane * 4u;
+	v6::decode_lanes<OWW, K>(src, dst, n_blocks, desc, status, counter, in_base, stage_base, ring_base, static_cast<int>(lane), hints);
+}
+constexpr int V6A_WARPS = 14, V6A_K = 3;   // 256-byte out rings: 15.5 KB per warp, fourteen warps = 66 304 lanes on 148 SMs
+constexpr int V6B_WARPS = 8, V6B_K = 4;    // 512-byte out rings: 24.5 KB per warp
 
 // K4: chains, one warp per chain, blocks in order; the output of a chain is flat, so a match
 // simply reads backwards across block boundaries of its frame.
@@ -882,6 +905,10 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 				     int(v5::WARPS * sizeof(v5::WarpMem)));
 		cudaFuncSetAttribute(decode_blocks_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v4::WARPS * sizeof(v4::WarpMem)));
+		cudaFuncSetAttribute(decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(v6::Layout<64, V6A_K>::smem_bytes(V6A_WARPS)));
+		cudaFuncSetAttribute(decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				     int(v6::Layout<128, V6B_K>::smem_bytes(V6B_WARPS)));
 	}
 	cudaEventCreate(&ctx->ev0);
 	cudaEventCreate(&ctx->ev1);
@@ -960,7 +987,8 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 {
 	if (!ctx || (blocks_per_warp != -1 && blocks_per_warp != 0 && blocks_per_warp != 1 && blocks_per_warp != 2 &&
 		     blocks_per_warp != 4 && blocks_per_warp != 8 && blocks_per_warp != 16 && blocks_per_warp != 64 && blocks_per_warp != 40 && blocks_per_warp != 41 &&
-		     blocks_per_warp != 42 && blocks_per_warp != 44 && blocks_per_warp != 48 && blocks_per_warp != 50))
+		     blocks_per_warp != 42 && blocks_per_warp != 44 && blocks_per_warp != 48 && blocks_per_warp != 50 && blocks_per_warp != 60 &&
+		     blocks_per_warp != 61))
 		return LZ4B200_ERR_ARG;
 	ctx->blocks_per_warp = blocks_per_warp;
 	return LZ4B200_OK;
@@ -985,7 +1013,7 @@ const char *lz4b200_k1_kernel_name(const lz4b200_ctx *ctx, uint32_t n_blocks)
 {
 	if (!ctx) return "";
 	const int g = k1_generation(ctx, n_blocks);
-	return g == 50 ? "decode_blocks_v5_kernel" : g >= 40 && g <= 48 ? "decode_blocks_v4_kernel" : g == 64 ? "decode_blocks_v3_kernel"
+	return g == 60 || g == 61 ? "decode_blocks_v6_kernel" : g == 50 ? "decode_blocks_v5_kernel" : g >= 40 && g <= 48 ? "decode_blocks_v4_kernel" : g == 64 ? "decode_blocks_v3_kernel"
 	       : g < 0 ? "decode_blocks_kernel" : "decode_blocks_v2_kernel";
 }
 
@@ -1110,6 +1138,40 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		per = per < 1 ? 1 : per > v3::MAX_NB ? v3::MAX_NB : per;
 		const uint32_t grid = (n_blocks + per - 1) / per;
 		decode_blocks_v3_kernel<<<grid, v3::CTA_THREADS, v3::SMEM_BYTES, ctx->stream>>>(src, dst, n_blocks, desc, status, per, ctx->d_prof);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		return LZ4B200_OK;
+	}
+	if (g == 60 || g == 61) {
+		// v6: persistent warps whose lanes pull blocks from a counter (one counter per stream lane of the context)
+		if (!ctx->d_counter) return LZ4B200_ERR_NOMEM;
+		int li = 0;
+		for (int i = 0; i < 4; i++)
+			if (ctx->lanes[i] == ctx->stream) li = i;
+		uint32_t *counter = ctx->d_counter + 16 * li;
+		CK(cudaMemsetAsync(counter, 0, 4, ctx->stream));
+		const uint32_t sms = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148);
+		// One CTA per SM.  A block is one lane's work from start to end, so a batch that fits the resident lanes runs
+		// as long as one block does: give each SM just the warps that hold the batch (the fewer share an SM, the
+		// shorter their trips); more blocks than 148 x WARPS x 32 lanes go round in turns.
+		const uint32_t warps = (n_blocks + 31) / 32;
+		const uint32_t max_w = g == 60 ? V6A_WARPS : V6B_WARPS;
+		uint32_t wpc = (warps + sms - 1) / sms;
+		wpc = wpc < 2 ? 2 : wpc > max_w ? max_w : wpc;
+		if (const char *e = getenv("LZ4B200_V6_WARPS")) {
+			const uint32_t w = static_cast<uint32_t>(atoi(e));
+			if (w >= 1 && w <= max_w) wpc = w;
+		}
+		uint32_t grid = (warps + wpc - 1) / wpc;
+		if (grid > sms) grid = sms;
+		uint32_t hints = 0;
+		if (const char *e = getenv("LZ4B200_V6_HINTS")) hints = static_cast<uint32_t>(atoi(e));
+		if (g == 60)
+			decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS><<<grid, wpc * 32, v6::Layout<64, V6A_K>::smem_bytes(V6A_WARPS), ctx->stream>>>(
+				src, dst, n_blocks, desc, status, counter, hints);
+		else
+			decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS><<<grid, wpc * 32, v6::Layout<128, V6B_K>::smem_bytes(V6B_WARPS), ctx->stream>>>(
+				src, dst, n_blocks, desc, status, counter, hints);
 		ctx->launches++;
 		CK(cudaGetLastError());
 		return LZ4B200_OK;

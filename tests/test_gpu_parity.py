@@ -467,7 +467,7 @@ def test_batch_exact_sizing(ctx, oracle):
         oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=1 << 21)
         assert (exc, msg, out) == (oexc, omsg, oout), (k, exc, msg, oexc, omsg)
 
-@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64, 40, 41, 48, 50])
+@pytest.mark.parametrize("g", [-1, 1, 2, 4, 8, 16, 64, 40, 41, 48, 50, 60, 61])
 def test_batch_k1_variants(ctx, oracle, g):
     """Every K1 variant (v1 one-warp-per-block, v2 with 1/2/4/8/16 blocks per warp, 64 = v3 CTA per block,
     40..48 = v4 warp per block with a shared-memory ring, 50 = v5 lane per block): good vectors,
@@ -735,7 +735,7 @@ def _py_decode(block):
     return bytes(out)
 
 
-@pytest.mark.parametrize("g", [-1, 1, 8, 16, 64, 41, 48, 50])
+@pytest.mark.parametrize("g", [-1, 1, 8, 16, 64, 41, 48, 50, 60, 61])
 def test_k1_overlap_matrix_direct(ctx, oracle, g):
     """lz4b200_decode_blocks on hand-made blocks: every offset 1..70 x match lengths around the
     warp / vector thresholds, at varying destination alignment (pattern replication, doubling)."""
@@ -869,7 +869,7 @@ def _v3_shape_blocks():
     return blocks
 
 
-@pytest.mark.parametrize("g", [64, 41, 44, 48, 50, 8, -1])
+@pytest.mark.parametrize("g", [64, 41, 44, 48, 50, 60, 61, 8, -1])
 def test_k1_v3_shapes_direct(ctx, oracle, g):
     """The shapes above through lz4b200_decode_blocks, compared with the pure-Python decoder (and with
     each other across kernel generations); destinations at every 16-byte phase."""
@@ -892,7 +892,7 @@ def test_k1_v3_many_blocks_property(ctx):
         assert out == data[(i % 13) * 1000:] + data[:(i % 13) * 1000], i
 
 
-@pytest.mark.parametrize("g", [50, 41])
+@pytest.mark.parametrize("g", [50, 60, 61, 41])
 def test_k1_lane_refill_and_checksums_direct(ctx, oracle, g):
     """300 blocks from 1 byte to 64 KiB (text, RLE, noise) with block checksums through lz4b200_decode_blocks:
     v5 lanes finish at very different times and pull new blocks from the counter; every third block's checksum

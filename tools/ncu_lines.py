@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--so", default="bo_lz4_ada_b200/liblz4b200.so")
     ap.add_argument("--by", default="inst", choices=["inst", "samples"])
+    ap.add_argument("--cubin-kernel", default=None, help="substring of the MANGLED name in the cubin (template instantiations)")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -69,7 +70,7 @@ def main():
             break
         if len(r) == len(hdr):
             body.append(r)
-    sass = sass_lines(args.so, args.kernel)
+    sass = sass_lines(args.so, args.cubin_kernel or args.kernel)
     if len(sass) != len(body):
         print("warning: %d SASS instructions in the cubin, %d in the report" % (len(sass), len(body)), file=sys.stderr)
     agg = collections.defaultdict(lambda: [0, 0, 0, collections.Counter()])
