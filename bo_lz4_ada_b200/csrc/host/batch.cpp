@@ -195,10 +195,11 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			if ((*sized_len)[i] != 0xffffffffu) known[b->presize[i]] = (*sized_len)[i];   // 0xffffffff: K5 gave up on it
 	b->chains.clear();
 	b->hash_frames.clear();
-	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of
-	// them a warp: measured against a CTA each from the pipelined chain kernel, K1 is level for 256 x 4 MiB text
-	// (40 ms vs 34 ms), 4x faster for 1024 mixed legacy / concatenated streams (5 ms vs 21 ms) and 2.6x faster on
-	// the 16 GiB mixed corpus.  LZ4B200_SOLO=1 turns the chain-per-block placement back on (A/B switch).
+	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of them a
+	// warp: what such a block costs is its serial depth (~100 MB/s per stream whichever kernel walks it -- K1 v4, the
+	// K4 pipeline and the round-based K6 all measure within 10 % of each other), so the shape that
+	// keeps the most streams resident wins: 2 960 warps of K1 against 148 - 296 CTAs of a chain kernel.
+	// LZ4B200_SOLO=1 turns the chain-per-block placement on (A/B switch; not RLE-like blocks only).
 	static const bool solo_on = [] {
 		const char *e = getenv("LZ4B200_SOLO");
 		return e && e[0] == '1';
@@ -245,7 +246,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO | LZ4B200_BLK_RING_CAP);
 				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
-				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max) {
+				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max && uint64_t(d.src_len) * 16 >= d.dst_cap) {
 					d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO;
 					lz4b200_chain c;
 					c.first_block = fp.first_block + i;
@@ -288,6 +289,33 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 	b->out_bytes = std::max(b->out_bytes, cursor);   // never shrinks: callers allocate from the first answer
 	b->spill_cursor = b->out_bytes;
 	b->placed = true;
+}
+
+// Blocks of [b0, b1) that suit the lane-per-block K1: compressed, of some size, up to 256 KiB of output, not RLE-like.
+uint64_t heavy_blocks(const lz4ada_batch *b, size_t b0, size_t b1)
+{
+	uint64_t n = 0;
+	for (size_t i = b0; i < b1; i++) {
+		const lz4b200_blk_desc &d = b->descs[i];
+		if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_CHAINED | LZ4B200_BLK_HASH_ONLY)) && d.src_len >= 4096 && d.dst_cap <= 262144 &&
+		    uint64_t(d.src_len) * 16 >= d.dst_cap)
+			n++;
+	}
+	return n;
+}
+
+// K1 over blocks [b0, b1): the block-count rule of lz4b200_decode_blocks, overridden towards the warp-per-block
+// kernel when too few of the blocks suit the lane-per-block one.
+int launch_k1(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev, size_t b0, size_t b1, uint64_t heavy)
+{
+	lz4b200_ctx *ctx = b->ctx;
+	const int saved_tuning = lz4b200_get_tuning(ctx);
+	const bool force_v4 = saved_tuning == 0 && heavy < 16384;
+	if (force_v4) lz4b200_set_tuning(ctx, 40);
+	b->k1_name = lz4b200_k1_kernel_name(ctx, uint32_t(b1 - b0));
+	const int rc = lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(b1 - b0), b->d_desc + b0, b->d_status + b0);
+	if (force_v4) lz4b200_set_tuning(ctx, saved_tuning);
+	return rc;
 }
 
 Raised device_fail(lz4ada_batch *b)
@@ -815,28 +843,14 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 		if (lz4b200_memset(ctx, b->d_status, 0xff, sizeof(lz4b200_blk_status) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		lz4b200_event_record(ctx, b->ev[0]);
 		{
-			// K1's own rule picks the lane-per-block kernel (v5) from the block count alone.  What fills its 75 776
-			// lanes, though, are the blocks that take long -- compressed ones of some size; stored blocks and RLE-like
-			// ones are over in microseconds and park a whole warp meanwhile.  With too few long blocks every lane
-			// decodes at most one and the launch lasts as long as that block (2 GiB of thirds text / RLE / random in
-			// 64 KiB blocks: 17.5 ms with v5, 5.6 ms with v4), so the host, which has the table, decides.
-			if (b->heavy_blocks < 0) {
-				int64_t n_heavy = 0;
-				for (const lz4b200_blk_desc &d : b->descs)
-					if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_CHAINED | LZ4B200_BLK_HASH_ONLY)) && d.src_len >= 4096 &&
-					    uint64_t(d.src_len) * 16 >= d.dst_cap)
-						n_heavy++;
-				b->heavy_blocks = n_heavy;
-			}
-			const uint64_t heavy = uint64_t(b->heavy_blocks);
-			const int sms = lz4b200_sm_count(ctx) > 0 ? lz4b200_sm_count(ctx) : 148;
-			const uint64_t lanes = uint64_t(sms) * 16 * 32;
-			const int saved_tuning = lz4b200_get_tuning(ctx);
-			const bool force_v4 = saved_tuning == 0 && heavy < lanes / 2 + lanes / 8;
-			if (force_v4) lz4b200_set_tuning(ctx, 40);
-			b->k1_name = lz4b200_k1_kernel_name(ctx, uint32_t(nb));
-			const int rc1 = lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(nb), b->d_desc, b->d_status);
-			if (force_v4) lz4b200_set_tuning(ctx, saved_tuning);
+			// K1's own rule picks the lane-per-block kernel (v6) from the block count alone.  What its lanes are good at,
+			// though, are blocks of up to 256 KiB that take long -- compressed ones of some size; stored blocks and
+			// RLE-like ones are over in microseconds (and in v6 park a whole warp meanwhile), and a multi-megabyte block
+			// in ONE lane would take a second.  With too few suitable blocks the launch lasts as long as one of them
+			// while most lanes idle (2 GiB of thirds text / RLE / random in 64 KiB blocks: 17.5 ms lane-per-block,
+			// 5.6 ms warp-per-block), so the host, which has the table, decides.
+			if (b->heavy_blocks < 0) b->heavy_blocks = int64_t(heavy_blocks(b, 0, nb));
+			const int rc1 = launch_k1(b, src_dev, dst_dev, 0, nb, uint64_t(b->heavy_blocks));
 			if (rc1 != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		}
 		lz4b200_event_record(ctx, b->ev[1]);
@@ -923,7 +937,7 @@ int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t
 		if (b1 > b0)
 			bad = bad || lz4b200_memset(ctx, b->d_status + b0, 0xff, sizeof(lz4b200_blk_status) * (b1 - b0)) != LZ4B200_OK;
 		if (b1 > b0)
-			bad = bad || lz4b200_decode_blocks(ctx, src_dev, dst_dev, b1 - b0, b->d_desc + b0, b->d_status + b0) != LZ4B200_OK;
+			bad = bad || launch_k1(b, src_dev, dst_dev, b0, b1, heavy_blocks(b, b0, b1)) != LZ4B200_OK;
 		// chains and frame tables index blocks globally, so they get the un-offset arrays
 		if (ncc)
 			bad = bad || lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(ncc), b->d_chains + c0, b->d_desc, b->d_status) != LZ4B200_OK;
@@ -1099,7 +1113,7 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 	if (b->placed && b->descs.size()) {
 		// fast shape: placement is known without touching the device -> pipeline H2D / kernels / D2H
 		rc = lz4ada_batch_upload(b, nullptr, nullptr);   // tables only
-		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 29)));   // ~512 MiB of output each
+		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 30)));   // ~1 GiB of output each: 16 384 blocks of 64 KiB, enough for the lane-per-block K1
 		if (rc == LZ4ADA_OK) rc = lz4ada_batch_run_pipelined(b, src_host, dst_host, d_src, d_dst, chunks);
 	} else {
 		rc = lz4ada_batch_upload(b, src_host, d_src);

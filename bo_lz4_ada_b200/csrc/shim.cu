@@ -15,6 +15,7 @@
 #include "kernels_v4.cuh"
 #include "kernels_v5.cuh"
 #include "kernels_v6.cuh"
+#include "kernels_k6.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -123,9 +124,10 @@ __device__ __forceinline__ uint32_t ring_block_cap(const lz4b200_blk_desc &d, ui
 template <uint32_t OWW, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 decode_blocks_v6_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_blocks,
-			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t *counter, uint32_t hints)
+			const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t *counter)
 {
-	// one CTA per SM; the launch picks its number of warps (<= WARPS) from the block count
+	// one CTA per SM and launch; the launch picks its number of warps (<= WARPS) from the block count and asks for
+	// just their shared memory, so that the launches of several chunks (other streams) can share an SM
 	extern __shared__ __align__(16) uint8_t v6_smem[];
 	using L = v6::Layout<OWW, K>;
 	const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(v6_smem));
@@ -133,9 +135,9 @@ decode_blocks_v6_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t 
 	const uint32_t side = s0 + warp * L::SIDE_WARP;
 	const uint32_t in_base = side + lane * v6::IN_STRIDE;
 	const uint32_t stage_base = side + L::IN_WARP + lane * v6::STAGE_SLOT;
-	const uint32_t rings0 = (s0 + WARPS * L::SIDE_WARP + L::OUT_WARP - 1u) & ~(L::OUT_WARP - 1u);
+	const uint32_t rings0 = (s0 + (blockDim.x >> 5) * L::SIDE_WARP + L::OUT_WARP - 1u) & ~(L::OUT_WARP - 1u);
 	const uint32_t ring_base = rings0 + warp * L::OUT_WARP + lane * 4u;
-	v6::decode_lanes<OWW, K>(src, dst, n_blocks, desc, status, counter, in_base, stage_base, ring_base, static_cast<int>(lane), hints);
+	v6::decode_lanes<OWW, K>(src, dst, n_blocks, desc, status, counter, in_base, stage_base, ring_base, static_cast<int>(lane));
 }
 constexpr int V6A_WARPS = 14, V6A_K = 3;   // 256-byte out rings: 15.5 KB per warp, fourteen warps = 66 304 lanes on 148 SMs
 constexpr int V6B_WARPS = 8, V6B_K = 4;    // 512-byte out rings: 24.5 KB per warp
@@ -244,6 +246,282 @@ struct PipeShared {
 __device__ __forceinline__ uint32_t vload(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void vstore(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
+// K4 / K6 parser role (one warp): walks the token chains of the chain's blocks -- a speculative parallel parse, 32
+// lanes x SPEC_SEG-byte segments, merge-verified, with a serial fallback -- and publishes batches of 32 sequences
+// into the shared-memory ring of `ps`.
+__device__ __forceinline__ void pipe_parser_role(PipeShared &ps, const lz4b200_chain &ch, const uint8_t *__restrict__ src, uint8_t *out,
+						 const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, int lane)
+{
+	uint64_t pos = 0, frame_start = 0;   // chain-relative
+	uint32_t ring = 0;                   // Output_Pos of the reference's Buffer (LZ4B200_BLK_RING_CAP blocks)
+	uint32_t k = 0;                      // batches published
+	bool stop = false;
+	for (uint32_t i = 0; i < ch.n_blocks && !stop; i++) {
+		const uint32_t b = ch.first_block + i;
+		const lz4b200_blk_desc d = desc[b];
+		if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
+		const uint64_t fpos0 = pos - frame_start;
+		const uint64_t room = ch.dst_cap - pos;
+		const uint32_t blk_cap = ring_block_cap(d, ring);
+		const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
+		const uint8_t *s = src + d.src_off;
+		const bool stored = (d.flags & LZ4B200_BLK_STORED) != 0;
+		const bool ordinary = !(d.flags & LZ4B200_BLK_HASH_ONLY) && fpos0 + cap < 0xfff00000ull &&
+				      !(stored && d.src_len > cap);
+		uint32_t computed = 0, declared = 0;
+		bool okay = ordinary;
+		if (okay && (d.flags & LZ4B200_BLK_HAS_CHECKSUM)) {
+			const uint8_t *t = s + d.src_len;
+			declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+			computed = quad_xxh32_prologue(s, d.src_len, lane);
+			okay = computed == declared;
+		}
+		uint32_t fpos = static_cast<uint32_t>(fpos0);
+		if (okay && stored) {
+			// stored block (lib/lz4ada.adb:685-695): no dependencies, the parser warp copies it itself
+			warp_copy<true>(out + pos, s, d.src_len, lane);
+			fpos += d.src_len;
+		} else if (okay) {
+			uint32_t ip = 0;
+			const uint32_t n = d.src_len;
+			uint32_t spec_backoff = 0;
+			while (ip < n && okay) {
+				// ---- speculative parallel parse of the next window (32 segments, one lane each) ----
+				if (spec_backoff == 0 && n - ip >= 4 * SPEC_SEG) {
+					const uint32_t wbase = ip;
+					const uint32_t seg_lo = wbase + lane * SPEC_SEG;
+					const uint32_t seg_hi = seg_lo + SPEC_SEG < n ? seg_lo + SPEC_SEG : n;
+					// pass 1: walk from a guessed token start (lane 0: the true one), publish the first positions
+					uint32_t p = seg_lo, cntv = 0;
+					bool dead = seg_lo >= n;
+					while (!dead && p < seg_hi) {
+						uint32_t lp, lit, ml, nx;
+						if (!parse_token(s, n, p, lp, lit, ml, nx)) { dead = true; break; }
+						if (cntv < SPEC_VIS) ps.vis[lane][cntv] = static_cast<uint16_t>(p - wbase);
+						cntv++;
+						p = nx;
+					}
+					const uint32_t exit_pos = p;
+					const uint32_t nvis = cntv < SPEC_VIS ? cntv : SPEC_VIS;
+					__syncwarp();
+					// verification: lane j walks on from its exit until it stands on a position lane j + 1 also
+					// visited -- from there on both parse identically, so lane j + 1 is in sync from that token
+					const uint32_t nvis_next = __shfl_down_sync(FULL_MASK, nvis, 1);
+					const uint32_t lo_next = seg_lo + SPEC_SEG;
+					const bool next_exists = lane < 31 && lo_next < n;
+					uint32_t bnext = 0xffffffffu;
+					bool merged = false;
+					if (!dead) {
+						if (!next_exists || exit_pos >= n) {
+							merged = true;
+							bnext = exit_pos;
+						} else {
+							uint32_t q = exit_pos, kk = 0;
+							for (uint32_t step = 0; step < 2 * SPEC_VIS; step++) {
+								while (kk < nvis_next && wbase + ps.vis[lane + 1][kk] < q) kk++;
+								if (kk >= nvis_next) break;
+								if (wbase + ps.vis[lane + 1][kk] == q) { merged = true; bnext = q; break; }
+								uint32_t lp, lit, ml, nx;
+								if (q >= lo_next + SPEC_SEG || !parse_token(s, n, q, lp, lit, ml, nx)) break;
+								q = nx;
+							}
+						}
+					}
+					const uint32_t last_lane = (n - 1 - wbase) / SPEC_SEG < 31 ? (n - 1 - wbase) / SPEC_SEG : 31;
+					const uint32_t need_mask = last_lane >= 31 ? 0xffffffffu : ((2u << last_lane) - 1u);
+					const uint32_t ok_mask = __ballot_sync(FULL_MASK, merged);
+					bool spec_ok = (ok_mask & need_mask) == need_mask;
+					uint32_t b_start = __shfl_up_sync(FULL_MASK, bnext, 1);
+					if (lane == 0) b_start = wbase;
+					const bool mine = static_cast<uint32_t>(lane) <= last_lane;
+					// pass 2: count the true tokens of [b_start, bnext)
+					uint32_t cnt_t = 0, out_t = 0;
+					if (spec_ok && mine) {
+						uint32_t q = b_start;
+						while (q < bnext) {
+							uint32_t lp, lit, ml, nx;
+							if (!parse_token(s, n, q, lp, lit, ml, nx)) { cnt_t = 0xffffffffu; break; }
+							cnt_t++;
+							out_t += lit + ml;
+							q = nx;
+						}
+						if (cnt_t != 0xffffffffu && q != bnext) cnt_t = 0xffffffffu;
+					}
+					if (__any_sync(FULL_MASK, cnt_t == 0xffffffffu)) spec_ok = false;
+					if (spec_ok) {
+						uint32_t icnt = cnt_t, iout = out_t;
+#pragma unroll
+						for (int sh = 1; sh < 32; sh <<= 1) {
+							const uint32_t a = __shfl_up_sync(FULL_MASK, icnt, sh), bsum = __shfl_up_sync(FULL_MASK, iout, sh);
+							if (lane >= sh) { icnt += a; iout += bsum; }
+						}
+						const uint32_t tot_cnt = __shfl_sync(FULL_MASK, icnt, 31), tot_out = __shfl_sync(FULL_MASK, iout, 31);
+						const uint32_t nb = (tot_cnt + 31) / 32;
+						const uint32_t used = fpos - static_cast<uint32_t>(fpos0);
+						if (tot_out > cap - used || nb > PIPE_SLOTS - 32 || tot_cnt == 0) {
+							spec_ok = false;   // capacity: the exact path reports it; nb: never with 256-byte segments
+						} else {
+							if (lane == 0) {
+								while (k + nb - vload(&ps.done_upto) > PIPE_SLOTS) __nanosleep(40);
+							}
+							__syncwarp();
+							if (vload(&ps.fail) != 0) { okay = false; break; }
+							// pass 3: emit descriptors straight into the ring at their global sequence index
+							if (mine) {
+								uint32_t idx = icnt - cnt_t, opos = fpos + (iout - out_t), q = b_start;
+								while (q < bnext) {
+									uint32_t lp, lit, ml, nx;
+									parse_token(s, n, q, lp, lit, ml, nx);
+									const uint32_t sl = (k + (idx >> 5)) % PIPE_SLOTS;
+									*reinterpret_cast<uint2 *>(&ps.sd[sl][idx & 31]) = make_uint2(lp, lit | (ml << 16));
+									if ((idx & 31) == 0) {
+										ps.count[sl] = tot_cnt - idx < 32 ? tot_cnt - idx : 32;
+										ps.out_start[sl] = opos;
+										ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
+										ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
+										ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
+										ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
+										ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
+										ps.blk[sl] = b;
+									}
+									idx++;
+									opos += lit + ml;
+									q = nx;
+								}
+							}
+							__syncwarp();
+							__threadfence_block();
+							if (lane == 0) vstore(&ps.produced, k + nb);
+							k += nb;
+							fpos += tot_out;
+							ip = __shfl_sync(FULL_MASK, bnext, last_lane);
+							continue;
+						}
+					}
+					spec_backoff = 8;   // segments did not re-synchronise here (long literal runs): go serial for a while
+				}
+				if (spec_backoff) spec_backoff--;
+				// ---- serial: wait for a free slot (lane 0 polls), then parse up to 32 sequences into it ----
+				uint32_t cnt = 0, total = 0;
+				bool fb = false;
+				// the idle lanes pull the next kilobyte of the compressed stream towards L1 so that the
+				// token chain walked by lane 0 does not pay a DRAM round trip every 128 bytes
+				if (lane >= 1 && lane <= 8 && ip + 128u * lane < n)
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(s + ip + 128u * lane));
+				if (lane == 0) {
+					// every published batch is eventually marked done (copied or skipped), so this ends
+					while (k - vload(&ps.done_upto) >= PIPE_SLOTS) __nanosleep(40);
+					SeqDesc *my = ps.sd[k % PIPE_SLOTS];
+					if (vload(&ps.fail) != 0) fb = true;   // a copier gave up: stop feeding
+					while (!fb && cnt < 32 && ip < n) {
+						const uint32_t t = ld_u8<true>(s + ip);
+						uint32_t lit = t >> 4, ml = t & 15, p = ip + 1, nxt;
+						if (lit == 15 || ml == 15) {
+							if (!parse_extended(s, n, p, lit, ml, nxt)) { fb = true; break; }
+						} else {
+							const uint32_t q = p + lit;
+							if (q + 2 <= n) { ml += 4; nxt = q + 2; }
+							else if (q == n && ml == 0) { nxt = n; }
+							else { fb = true; break; }
+						}
+						*reinterpret_cast<uint2 *>(my + cnt) = make_uint2(p, lit | (ml << 16));
+						cnt++;
+						total += lit + ml;
+						ip = nxt;
+					}
+					if (total > cap - (fpos - static_cast<uint32_t>(fpos0))) fb = true;   // exact path reports it
+					if (!fb && cnt) {
+						const uint32_t sl = k % PIPE_SLOTS;
+						ps.count[sl] = cnt;
+						ps.out_start[sl] = fpos;
+						ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
+						ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
+						ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
+						ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
+						ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
+						ps.blk[sl] = b;
+						__threadfence_block();
+						vstore(&ps.produced, k + 1);
+					}
+				}
+				fb = __shfl_sync(FULL_MASK, fb ? 1 : 0, 0) != 0;
+				cnt = __shfl_sync(FULL_MASK, cnt, 0);
+				total = __shfl_sync(FULL_MASK, total, 0);
+				ip = __shfl_sync(FULL_MASK, ip, 0);
+				if (fb || vload(&ps.fail) != 0) { okay = false; break; }
+				if (cnt) { k++; fpos += total; }
+			}
+		}
+		if (okay) {
+			// provisional: stands unless a copier gives up on one of this block's batches
+			if (lane == 0) {
+				status[b].code = LZ4B200_ST_OK;
+				status[b].out_len = fpos - static_cast<uint32_t>(fpos0);
+				status[b].err_pos = 0;
+				status[b].aux = 0;
+				status[b].xxh32_computed = computed;
+				status[b].xxh32_declared = declared;
+			}
+			pos += fpos - static_cast<uint32_t>(fpos0);
+			ring += fpos - static_cast<uint32_t>(fpos0);
+		} else {
+			// anything out of the ordinary: drain the pipeline, then the exact routine takes over from this block
+			if (lane == 0 && vload(&ps.fail_block) == 0xffffffffu) atomicMin(&ps.fail_block, i);
+			stop = true;
+		}
+	}
+	if (lane == 0) {
+		__threadfence_block();
+		vstore(&ps.end_batch, k);
+	}
+}
+
+// The exact routine from the first block the fast path gave up on (one warp, after the pipeline has drained).
+__device__ __forceinline__ void pipe_exact_tail(PipeShared &ps, const lz4b200_chain &ch, const uint8_t *__restrict__ src, uint8_t *out,
+						const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, int lane)
+{
+	const int warp = 0;
+	const uint32_t fbk = ps.fail_block;
+	if (fbk != 0xffffffffu && warp == 0) {
+		uint64_t pos = 0, frame_start = 0;
+		uint32_t ring = 0;
+		bool failed = false;
+		for (uint32_t i = 0; i < ch.n_blocks; i++) {
+			const uint32_t b = ch.first_block + i;
+			const lz4b200_blk_desc d = desc[b];
+			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
+			if (i < fbk) {   // finished by the pipeline
+				ring_block_cap(d, ring);   // (the cursor's wrap at this block's start)
+				pos += status[b].out_len;
+				ring += status[b].out_len;
+				continue;
+			}
+			if (failed) {
+				if (lane == 0) {
+					status[b].code = LZ4B200_ST_NOT_RUN;
+					status[b].out_len = 0; status[b].err_pos = 0; status[b].aux = 0;
+					status[b].xxh32_computed = 0; status[b].xxh32_declared = 0;
+				}
+				continue;
+			}
+			const uint64_t fpos = pos - frame_start;
+			const uint64_t room = ch.dst_cap - pos;
+			const uint32_t blk_cap = ring_block_cap(d, ring);
+			const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
+			if (d.flags & LZ4B200_BLK_SOLO) {
+				// a chain of one block taken out of an independent frame: independent semantics
+				process_block<false>(src, out + pos, d, cap, d.hist_avail, status + b, lane);
+			} else {
+				const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
+				process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
+			}
+			__syncwarp();
+			if (status[b].code != LZ4B200_ST_OK) failed = true;
+			else { pos += status[b].out_len; ring += status[b].out_len; }
+		}
+	}
+}
+
 __global__ void __launch_bounds__(PIPE_WARPS * 32)
 decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_chains,
 			 const lz4b200_chain *__restrict__ chains, const lz4b200_blk_desc *__restrict__ desc,
@@ -263,229 +541,7 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 	__syncthreads();
 
 	if (warp == 0) {
-		// ---------------- parser ----------------
-		uint64_t pos = 0, frame_start = 0;   // chain-relative
-		uint32_t ring = 0;                   // Output_Pos of the reference's Buffer (LZ4B200_BLK_RING_CAP blocks)
-		uint32_t k = 0;                      // batches published
-		bool stop = false;
-		for (uint32_t i = 0; i < ch.n_blocks && !stop; i++) {
-			const uint32_t b = ch.first_block + i;
-			const lz4b200_blk_desc d = desc[b];
-			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
-			const uint64_t fpos0 = pos - frame_start;
-			const uint64_t room = ch.dst_cap - pos;
-			const uint32_t blk_cap = ring_block_cap(d, ring);
-			const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
-			const uint8_t *s = src + d.src_off;
-			const bool stored = (d.flags & LZ4B200_BLK_STORED) != 0;
-			const bool ordinary = !(d.flags & LZ4B200_BLK_HASH_ONLY) && fpos0 + cap < 0xfff00000ull &&
-					      !(stored && d.src_len > cap);
-			uint32_t computed = 0, declared = 0;
-			bool okay = ordinary;
-			if (okay && (d.flags & LZ4B200_BLK_HAS_CHECKSUM)) {
-				const uint8_t *t = s + d.src_len;
-				declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
-				computed = quad_xxh32_prologue(s, d.src_len, lane);
-				okay = computed == declared;
-			}
-			uint32_t fpos = static_cast<uint32_t>(fpos0);
-			if (okay && stored) {
-				// stored block (lib/lz4ada.adb:685-695): no dependencies, the parser warp copies it itself
-				warp_copy<true>(out + pos, s, d.src_len, lane);
-				fpos += d.src_len;
-			} else if (okay) {
-				uint32_t ip = 0;
-				const uint32_t n = d.src_len;
-				uint32_t spec_backoff = 0;
-				while (ip < n && okay) {
-					// ---- speculative parallel parse of the next window (32 segments, one lane each) ----
-					if (spec_backoff == 0 && n - ip >= 4 * SPEC_SEG) {
-						const uint32_t wbase = ip;
-						const uint32_t seg_lo = wbase + lane * SPEC_SEG;
-						const uint32_t seg_hi = seg_lo + SPEC_SEG < n ? seg_lo + SPEC_SEG : n;
-						// pass 1: walk from a guessed token start (lane 0: the true one), publish the first positions
-						uint32_t p = seg_lo, cntv = 0;
-						bool dead = seg_lo >= n;
-						while (!dead && p < seg_hi) {
-							uint32_t lp, lit, ml, nx;
-							if (!parse_token(s, n, p, lp, lit, ml, nx)) { dead = true; break; }
-							if (cntv < SPEC_VIS) ps.vis[lane][cntv] = static_cast<uint16_t>(p - wbase);
-							cntv++;
-							p = nx;
-						}
-						const uint32_t exit_pos = p;
-						const uint32_t nvis = cntv < SPEC_VIS ? cntv : SPEC_VIS;
-						__syncwarp();
-						// verification: lane j walks on from its exit until it stands on a position lane j + 1 also
-						// visited -- from there on both parse identically, so lane j + 1 is in sync from that token
-						const uint32_t nvis_next = __shfl_down_sync(FULL_MASK, nvis, 1);
-						const uint32_t lo_next = seg_lo + SPEC_SEG;
-						const bool next_exists = lane < 31 && lo_next < n;
-						uint32_t bnext = 0xffffffffu;
-						bool merged = false;
-						if (!dead) {
-							if (!next_exists || exit_pos >= n) {
-								merged = true;
-								bnext = exit_pos;
-							} else {
-								uint32_t q = exit_pos, kk = 0;
-								for (uint32_t step = 0; step < 2 * SPEC_VIS; step++) {
-									while (kk < nvis_next && wbase + ps.vis[lane + 1][kk] < q) kk++;
-									if (kk >= nvis_next) break;
-									if (wbase + ps.vis[lane + 1][kk] == q) { merged = true; bnext = q; break; }
-									uint32_t lp, lit, ml, nx;
-									if (q >= lo_next + SPEC_SEG || !parse_token(s, n, q, lp, lit, ml, nx)) break;
-									q = nx;
-								}
-							}
-						}
-						const uint32_t last_lane = (n - 1 - wbase) / SPEC_SEG < 31 ? (n - 1 - wbase) / SPEC_SEG : 31;
-						const uint32_t need_mask = last_lane >= 31 ? 0xffffffffu : ((2u << last_lane) - 1u);
-						const uint32_t ok_mask = __ballot_sync(FULL_MASK, merged);
-						bool spec_ok = (ok_mask & need_mask) == need_mask;
-						uint32_t b_start = __shfl_up_sync(FULL_MASK, bnext, 1);
-						if (lane == 0) b_start = wbase;
-						const bool mine = static_cast<uint32_t>(lane) <= last_lane;
-						// pass 2: count the true tokens of [b_start, bnext)
-						uint32_t cnt_t = 0, out_t = 0;
-						if (spec_ok && mine) {
-							uint32_t q = b_start;
-							while (q < bnext) {
-								uint32_t lp, lit, ml, nx;
-								if (!parse_token(s, n, q, lp, lit, ml, nx)) { cnt_t = 0xffffffffu; break; }
-								cnt_t++;
-								out_t += lit + ml;
-								q = nx;
-							}
-							if (cnt_t != 0xffffffffu && q != bnext) cnt_t = 0xffffffffu;
-						}
-						if (__any_sync(FULL_MASK, cnt_t == 0xffffffffu)) spec_ok = false;
-						if (spec_ok) {
-							uint32_t icnt = cnt_t, iout = out_t;
-#pragma unroll
-							for (int sh = 1; sh < 32; sh <<= 1) {
-								const uint32_t a = __shfl_up_sync(FULL_MASK, icnt, sh), bsum = __shfl_up_sync(FULL_MASK, iout, sh);
-								if (lane >= sh) { icnt += a; iout += bsum; }
-							}
-							const uint32_t tot_cnt = __shfl_sync(FULL_MASK, icnt, 31), tot_out = __shfl_sync(FULL_MASK, iout, 31);
-							const uint32_t nb = (tot_cnt + 31) / 32;
-							const uint32_t used = fpos - static_cast<uint32_t>(fpos0);
-							if (tot_out > cap - used || nb > PIPE_SLOTS - 32 || tot_cnt == 0) {
-								spec_ok = false;   // capacity: the exact path reports it; nb: never with 256-byte segments
-							} else {
-								if (lane == 0) {
-									while (k + nb - vload(&ps.done_upto) > PIPE_SLOTS) __nanosleep(40);
-								}
-								__syncwarp();
-								if (vload(&ps.fail) != 0) { okay = false; break; }
-								// pass 3: emit descriptors straight into the ring at their global sequence index
-								if (mine) {
-									uint32_t idx = icnt - cnt_t, opos = fpos + (iout - out_t), q = b_start;
-									while (q < bnext) {
-										uint32_t lp, lit, ml, nx;
-										parse_token(s, n, q, lp, lit, ml, nx);
-										const uint32_t sl = (k + (idx >> 5)) % PIPE_SLOTS;
-										*reinterpret_cast<uint2 *>(&ps.sd[sl][idx & 31]) = make_uint2(lp, lit | (ml << 16));
-										if ((idx & 31) == 0) {
-											ps.count[sl] = tot_cnt - idx < 32 ? tot_cnt - idx : 32;
-											ps.out_start[sl] = opos;
-											ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
-											ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
-											ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
-											ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
-											ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
-											ps.blk[sl] = b;
-										}
-										idx++;
-										opos += lit + ml;
-										q = nx;
-									}
-								}
-								__syncwarp();
-								__threadfence_block();
-								if (lane == 0) vstore(&ps.produced, k + nb);
-								k += nb;
-								fpos += tot_out;
-								ip = __shfl_sync(FULL_MASK, bnext, last_lane);
-								continue;
-							}
-						}
-						spec_backoff = 8;   // segments did not re-synchronise here (long literal runs): go serial for a while
-					}
-					if (spec_backoff) spec_backoff--;
-					// ---- serial: wait for a free slot (lane 0 polls), then parse up to 32 sequences into it ----
-					uint32_t cnt = 0, total = 0;
-					bool fb = false;
-					// the idle lanes pull the next kilobyte of the compressed stream towards L1 so that the
-					// token chain walked by lane 0 does not pay a DRAM round trip every 128 bytes
-					if (lane >= 1 && lane <= 8 && ip + 128u * lane < n)
-						asm volatile("prefetch.global.L1 [%0];" ::"l"(s + ip + 128u * lane));
-					if (lane == 0) {
-						// every published batch is eventually marked done (copied or skipped), so this ends
-						while (k - vload(&ps.done_upto) >= PIPE_SLOTS) __nanosleep(40);
-						SeqDesc *my = ps.sd[k % PIPE_SLOTS];
-						if (vload(&ps.fail) != 0) fb = true;   // a copier gave up: stop feeding
-						while (!fb && cnt < 32 && ip < n) {
-							const uint32_t t = ld_u8<true>(s + ip);
-							uint32_t lit = t >> 4, ml = t & 15, p = ip + 1, nxt;
-							if (lit == 15 || ml == 15) {
-								if (!parse_extended(s, n, p, lit, ml, nxt)) { fb = true; break; }
-							} else {
-								const uint32_t q = p + lit;
-								if (q + 2 <= n) { ml += 4; nxt = q + 2; }
-								else if (q == n && ml == 0) { nxt = n; }
-								else { fb = true; break; }
-							}
-							*reinterpret_cast<uint2 *>(my + cnt) = make_uint2(p, lit | (ml << 16));
-							cnt++;
-							total += lit + ml;
-							ip = nxt;
-						}
-						if (total > cap - (fpos - static_cast<uint32_t>(fpos0))) fb = true;   // exact path reports it
-						if (!fb && cnt) {
-							const uint32_t sl = k % PIPE_SLOTS;
-							ps.count[sl] = cnt;
-							ps.out_start[sl] = fpos;
-							ps.cap_abs[sl] = static_cast<uint32_t>(fpos0) + cap;
-							ps.frame_base_lo[sl] = static_cast<uint32_t>(frame_start);
-							ps.frame_base_hi[sl] = static_cast<uint32_t>(frame_start >> 32);
-							ps.src_lo[sl] = static_cast<uint32_t>(d.src_off);
-							ps.src_hi[sl] = static_cast<uint32_t>(d.src_off >> 32);
-							ps.blk[sl] = b;
-							__threadfence_block();
-							vstore(&ps.produced, k + 1);
-						}
-					}
-					fb = __shfl_sync(FULL_MASK, fb ? 1 : 0, 0) != 0;
-					cnt = __shfl_sync(FULL_MASK, cnt, 0);
-					total = __shfl_sync(FULL_MASK, total, 0);
-					ip = __shfl_sync(FULL_MASK, ip, 0);
-					if (fb || vload(&ps.fail) != 0) { okay = false; break; }
-					if (cnt) { k++; fpos += total; }
-				}
-			}
-			if (okay) {
-				// provisional: stands unless a copier gives up on one of this block's batches
-				if (lane == 0) {
-					status[b].code = LZ4B200_ST_OK;
-					status[b].out_len = fpos - static_cast<uint32_t>(fpos0);
-					status[b].err_pos = 0;
-					status[b].aux = 0;
-					status[b].xxh32_computed = computed;
-					status[b].xxh32_declared = declared;
-				}
-				pos += fpos - static_cast<uint32_t>(fpos0);
-				ring += fpos - static_cast<uint32_t>(fpos0);
-			} else {
-				// anything out of the ordinary: drain the pipeline, then the exact routine takes over from this block
-				if (lane == 0 && vload(&ps.fail_block) == 0xffffffffu) atomicMin(&ps.fail_block, i);
-				stop = true;
-			}
-		}
-		if (lane == 0) {
-			__threadfence_block();
-			vstore(&ps.end_batch, k);
-		}
+		pipe_parser_role(ps, ch, src, out, desc, status, lane);
 	} else {
 		// ---------------- copiers ----------------
 		uint8_t *tile = reinterpret_cast<uint8_t *>(tiles[warp]);
@@ -541,46 +597,79 @@ decode_chain_pipe_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t
 		}
 	}
 	__syncthreads();
-	// ---------------- exact routine from the first block the fast path gave up on ----------------
-	const uint32_t fbk = ps.fail_block;
-	if (fbk != 0xffffffffu && warp == 0) {
-		uint64_t pos = 0, frame_start = 0;
-		uint32_t ring = 0;
-		bool failed = false;
-		for (uint32_t i = 0; i < ch.n_blocks; i++) {
-			const uint32_t b = ch.first_block + i;
-			const lz4b200_blk_desc d = desc[b];
-			if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
-			if (i < fbk) {   // finished by the pipeline
-				ring_block_cap(d, ring);   // (the cursor's wrap at this block's start)
-				pos += status[b].out_len;
-				ring += status[b].out_len;
-				continue;
-			}
-			if (failed) {
-				if (lane == 0) {
-					status[b].code = LZ4B200_ST_NOT_RUN;
-					status[b].out_len = 0; status[b].err_pos = 0; status[b].aux = 0;
-					status[b].xxh32_computed = 0; status[b].xxh32_declared = 0;
-				}
-				continue;
-			}
-			const uint64_t fpos = pos - frame_start;
-			const uint64_t room = ch.dst_cap - pos;
-			const uint32_t blk_cap = ring_block_cap(d, ring);
-			const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
-			if (d.flags & LZ4B200_BLK_SOLO) {
-				// a chain of one block taken out of an independent frame: independent semantics
-				process_block<false>(src, out + pos, d, cap, d.hist_avail, status + b, lane);
-			} else {
-				const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
-				process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
-			}
-			__syncwarp();
-			if (status[b].code != LZ4B200_ST_OK) failed = true;
-			else { pos += status[b].out_len; ring += status[b].out_len; }
+	if (warp == 0) pipe_exact_tail(ps, ch, src, out, desc, status, lane);
+}
+
+// K6: one CTA of two warps per chain -- warp 0 parses in steps of 1 KiB of staged compressed bytes (pointer doubling
+// over a next-token table), warp 1 copies the batches in order, each in dependency rounds on a 64 KiB shared-memory
+// window of the chain's output (kernels_k6.cuh).
+constexpr uint32_t K6_SMEM = k6::WIN + ((sizeof(k6::Shared) + 15) & ~15u) + TILE_BYTES + 32 + 32 * sizeof(SeqDesc) + 64;
+
+// The exact routine from the first block the fast path gave up on (one warp, after the pipeline has drained).
+__device__ __forceinline__ void chain_exact_tail(uint32_t fbk, const lz4b200_chain &ch, const uint8_t *__restrict__ src, uint8_t *out,
+						 const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, int lane)
+{
+	if (fbk == 0xffffffffu) return;
+	uint64_t pos = 0, frame_start = 0;
+	uint32_t ring = 0;
+	bool failed = false;
+	for (uint32_t i = 0; i < ch.n_blocks; i++) {
+		const uint32_t b = ch.first_block + i;
+		const lz4b200_blk_desc d = desc[b];
+		if (d.flags & LZ4B200_BLK_FIRST_OF_FRAME) { frame_start = pos; ring = 0; }
+		if (i < fbk) {   // finished by the pipeline
+			ring_block_cap(d, ring);   // (the cursor's wrap at this block's start)
+			pos += status[b].out_len;
+			ring += status[b].out_len;
+			continue;
 		}
+		if (failed) {
+			if (lane == 0) {
+				status[b].code = LZ4B200_ST_NOT_RUN;
+				status[b].out_len = 0; status[b].err_pos = 0; status[b].aux = 0;
+				status[b].xxh32_computed = 0; status[b].xxh32_declared = 0;
+			}
+			continue;
+		}
+		const uint64_t fpos = pos - frame_start;
+		const uint64_t room = ch.dst_cap - pos;
+		const uint32_t blk_cap = ring_block_cap(d, ring);
+		const uint32_t cap = room < blk_cap ? static_cast<uint32_t>(room) : blk_cap;
+		if (d.flags & LZ4B200_BLK_SOLO) {
+			// a chain of one block taken out of an independent frame: independent semantics
+			process_block<false>(src, out + pos, d, cap, d.hist_avail, status + b, lane);
+		} else {
+			const uint32_t hist = fpos > 0xfffffffeull ? 0xffffffffu : static_cast<uint32_t>(fpos);
+			process_block<true>(src, out + pos, d, cap, hist, status + b, lane);
+		}
+		__syncwarp();
+		if (status[b].code != LZ4B200_ST_OK) failed = true;
+		else { pos += status[b].out_len; ring += status[b].out_len; }
 	}
+}
+
+__global__ void __launch_bounds__(64, 2)
+decode_chain_k6_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_chains,
+		       const lz4b200_chain *__restrict__ chains, const lz4b200_blk_desc *__restrict__ desc,
+		       lz4b200_blk_status *status, uint32_t dbg)
+{
+	extern __shared__ __align__(16) uint8_t k6_smem[];
+	k6::Shared &sh = *reinterpret_cast<k6::Shared *>(k6_smem + k6::WIN);
+	uint8_t *tile = k6_smem + k6::WIN + ((sizeof(k6::Shared) + 15) & ~size_t(15));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t c = blockIdx.x;
+	if (c >= n_chains) return;
+	const lz4b200_chain ch = chains[c];
+	uint8_t *out = dst + ch.dst_off;
+	if (threadIdx.x == 0) {
+		sh.produced = 0; sh.done_upto = 0; sh.fail = 0; sh.end_batch = 0xffffffffu; sh.fail_block = 0xffffffffu;
+		sh.copier_in = 0; sh.copier_blk = 0;
+	}
+	__syncthreads();
+	if (warp == 0) k6::parser_role(sh, ch, src, desc, status, lane);
+	else k6::copier_role(sh, static_cast<uint32_t>(__cvta_generic_to_shared(k6_smem)), tile, ch, src, out, lane, dbg);
+	__syncthreads();
+	if (warp == 0) chain_exact_tail(sh.fail_block, ch, src, out, desc, status, lane);
 }
 
 // One block against a device-resident history window (single-block path under Update).
@@ -905,6 +994,7 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 				     int(v5::WARPS * sizeof(v5::WarpMem)));
 		cudaFuncSetAttribute(decode_blocks_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v4::WARPS * sizeof(v4::WarpMem)));
+		cudaFuncSetAttribute(decode_chain_k6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(K6_SMEM));
 		cudaFuncSetAttribute(decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v6::Layout<64, V6A_K>::smem_bytes(V6A_WARPS)));
 		cudaFuncSetAttribute(decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1001,10 +1091,10 @@ static int k1_generation(const lz4b200_ctx *ctx, uint32_t n_blocks)
 {
 	int g = ctx->blocks_per_warp;
 	if (g == 0) {
-		// v5 (a lane per block) needs tens of thousands of blocks to fill the chip -- 148 SMs x 16 warps x 32
-		// lanes; below that v4 (a warp per block) is the faster shape
-		const uint32_t lanes = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16u * 32u;
-		g = n_blocks >= lanes / 2 + lanes / 8 ? 50 : 40;
+		// v6 (a lane per block) runs a batch in the time one block takes when the batch fits the resident lanes
+		// (148 SMs x 14 warps x 32), and that time does not shrink with the batch: ~5 ms for 64 KiB text blocks.
+		// v4 (a warp per block) costs ~0.33 us per such block, so it is the faster shape below ~16 000 blocks.
+		g = n_blocks >= 16384u ? 60 : 40;
 	}
 	return g;
 }
@@ -1164,14 +1254,12 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		}
 		uint32_t grid = (warps + wpc - 1) / wpc;
 		if (grid > sms) grid = sms;
-		uint32_t hints = 0;
-		if (const char *e = getenv("LZ4B200_V6_HINTS")) hints = static_cast<uint32_t>(atoi(e));
 		if (g == 60)
-			decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS><<<grid, wpc * 32, v6::Layout<64, V6A_K>::smem_bytes(V6A_WARPS), ctx->stream>>>(
-				src, dst, n_blocks, desc, status, counter, hints);
+			decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS><<<grid, wpc * 32, v6::Layout<64, V6A_K>::smem_bytes(wpc), ctx->stream>>>(
+				src, dst, n_blocks, desc, status, counter);
 		else
-			decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS><<<grid, wpc * 32, v6::Layout<128, V6B_K>::smem_bytes(V6B_WARPS), ctx->stream>>>(
-				src, dst, n_blocks, desc, status, counter, hints);
+			decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS><<<grid, wpc * 32, v6::Layout<128, V6B_K>::smem_bytes(wpc), ctx->stream>>>(
+				src, dst, n_blocks, desc, status, counter);
 		ctx->launches++;
 		CK(cudaGetLastError());
 		return LZ4B200_OK;
@@ -1248,13 +1336,22 @@ int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_chains == 0) return LZ4B200_OK;
 	// LZ4B200_CHAIN_KERNEL=warp selects the one-warp-per-chain kernel (A/B comparisons, tests)
-	static const bool warp_kernel = [] {
+	// The default is the K4 pipeline (one parser warp, seven gated copier warps).  LZ4B200_CHAIN_KERNEL=k6 selects K6
+	// (pointer-doubling parser + round-based copier on a shared-memory window: same speed per stream, kept for A/B and
+	// as the base of a many-warps-per-stream kernel), =warp the one-warp-per-chain kernel
+	static const int which = [] {
 		const char *e = getenv("LZ4B200_CHAIN_KERNEL");
-		return e && e[0] == 'w';
+		return e && e[0] == 'w' ? 1 : e && e[0] == 'k' ? 0 : 2;
 	}();
-	if (warp_kernel) {
+	if (which == 1) {
 		const uint32_t grid = (n_chains + K1_WARPS - 1) / K1_WARPS;
 		decode_linked_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+	} else if (which == 0) {
+		static const uint32_t dbg = [] {
+			const char *e = getenv("LZ4B200_K6_DBG");   // 1: the copier skips its copies (timing of the parser alone; output is wrong)
+			return e ? static_cast<uint32_t>(atoi(e)) : 0u;
+		}();
+		decode_chain_k6_kernel<<<n_chains, 64, K6_SMEM, ctx->stream>>>(src, dst, n_chains, chains, desc, status, dbg);
 	} else {
 		decode_chain_pipe_kernel<<<n_chains, PIPE_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
 	}
