@@ -27,6 +27,9 @@ private package LZ4Ada.Device is
    Blk_Hash_Only      : constant Unsigned_32 := 4;
    Blk_Chained        : constant Unsigned_32 := 8;
    Blk_First_Of_Frame : constant Unsigned_32 := 16;
+   Blk_Solo           : constant Unsigned_32 := 32;    --  chain of one block taken from an independent frame
+   Blk_Ring_Cap       : constant Unsigned_32 := 64;    --  Dst_Cap = the caller's Buffer length (lib/lz4ada.adb:54, 678-680)
+   Blk_K2             : constant Unsigned_32 := 128;   --  stored block routed to Copy_Stored; K1 skips it
 
    --  lz4b200_blk_status
    type Block_Status is record
@@ -51,6 +54,10 @@ private package LZ4Ada.Device is
 
    function Create (Device_Index : int; Cuda_Stream : System.Address; Ctx : out Context) return int
      with Import, Convention => C, External_Name => "lz4b200_create";
+   --  A context is reference counted: Create returns one reference, Destroy drops one, Retain takes one more (a
+   --  Limited_Controlled Decompressor holds its own, so finalisation order does not matter).
+   function Retain (Ctx : Context) return int
+     with Import, Convention => C, External_Name => "lz4b200_retain";
    function Destroy (Ctx : Context) return int
      with Import, Convention => C, External_Name => "lz4b200_destroy";
    function Last_Error (Ctx : Context) return Interfaces.C.Strings.chars_ptr
@@ -83,6 +90,16 @@ private package LZ4Ada.Device is
    function XXH32_Frames (Ctx : Context; Dst : System.Address; N_Frames : Unsigned_32;
                           Frames, Desc, Status, Digest, Valid : System.Address) return int
      with Import, Convention => C, External_Name => "lz4b200_xxh32_frames";
+   --  K3 over explicit byte ranges (content checksums of re-placed frames, block checksums of stored blocks)
+   type Hash_Span is record
+      Off, Len : Unsigned_64;
+   end record with Convention => C;
+   function XXH32_Spans (Ctx : Context; Data : System.Address; N : Unsigned_32; Spans, Digests : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_xxh32_spans";
+   --  K2: stored blocks as a wide copy (lib/lz4ada.adb:685-695), block checksums beside it
+   function Copy_Stored (Ctx : Context; Src, Dst : System.Address; N_Idx : Unsigned_32; Idx : System.Address;
+                         Max_Len : Unsigned_32; Desc, Status, Spans, Scratch : System.Address) return int
+     with Import, Convention => C, External_Name => "lz4b200_copy_stored";
    --  K5: size pre-pass
    function Size_Blocks (Ctx : Context; Src : System.Address; N_Blocks : Unsigned_32;
                          Desc, Status : System.Address) return int
@@ -99,6 +116,11 @@ private package LZ4Ada.Device is
                           Hash_Content : int; Host_Dst : System.Address; Dst_Cap : Unsigned_32;
                           Status : out Block_Status) return int
      with Import, Convention => C, External_Name => "lz4b200_stream_block";
+   --  ... with the frame's block maximum as a hint: one synchronisation per block instead of two
+   function Stream_Block2 (S : Stream; Host_Src : System.Address; Src_Len, Flags : Unsigned_32;
+                           Hash_Content : int; Host_Dst : System.Address; Dst_Cap, Expect_Out : Unsigned_32;
+                           Status : out Block_Status) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_block2";
    function Stream_Digest (S : Stream; XXH32 : out Unsigned_32) return int
      with Import, Convention => C, External_Name => "lz4b200_stream_digest";
    --  read-ahead under Update: N bytes decoded ahead of time by Decode_Blocks into a device staging buffer
@@ -106,8 +128,8 @@ private package LZ4Ada.Device is
    function Stream_Adopt (S : Stream; Dev_Bytes : System.Address; N : Unsigned_32; Hash_Content : int) return int
      with Import, Convention => C, External_Name => "lz4b200_stream_adopt";
 
-   --  which K1 kernel Decode_Blocks launches: 0 = chosen from the block count (v5 lane-per-block for batches that
-   --  fill the chip, v4 warp-per-block otherwise); see include/lz4b200.h for the other values
+   --  which K1 kernel Decode_Blocks launches: 0 = chosen from the block count (v6 lane-per-block from ~20 000
+   --  blocks on, v4 warp-per-block below); see include/lz4b200.h for the other values
    function Set_Tuning (Ctx : Context; Generation : int) return int
      with Import, Convention => C, External_Name => "lz4b200_set_tuning";
    function K1_Kernel_Name (Ctx : Context; N_Blocks : Unsigned_32) return Interfaces.C.Strings.chars_ptr

@@ -151,6 +151,9 @@ _SIGNATURES = {
     "lz4b200_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "lz4b200_copy_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_float)]),
+    "lz4b200_device_of": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_event_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "lz4b200_event_destroy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -172,6 +175,9 @@ _SIGNATURES = {
     "lz4b200_stream_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32,
                                             ctypes.POINTER(BlkStatus)]),
+    "lz4b200_stream_block2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.POINTER(BlkStatus)]),
     "lz4b200_stream_digest": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32)]),
     "lz4b200_stream_adopt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]),
     # LZ4Ada API
@@ -213,6 +219,10 @@ _SIGNATURES = {
     "lz4ada_batch_run_pipelined": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_uint32]),
     "lz4ada_batch_results": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(BatchResult)]),
+    "lz4ada_last_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "lz4ada_batch_decompress_multi": (ctypes.c_int, [ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_uint64,
+                                                     ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(BatchItem),
+                                                     ctypes.c_int, ctypes.POINTER(BatchResult), ctypes.c_char_p, ctypes.c_size_t]),
     "lz4ada_batch_message": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
     "lz4ada_batch_free": (None, [ctypes.c_void_p]),
     "lz4ada_batch_decompress": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
@@ -342,6 +352,13 @@ class DeviceContext:
 
     def sm_count(self):
         return lib().lz4b200_sm_count(self.handle)
+
+    def copy_probe(self, dst_dev, src_dev, nbytes, reps=5):
+        """GB/s (read + write) of a plain device copy: the roofline denominator, measured in place."""
+        ms = ctypes.c_float(0)
+        self._ck(lib().lz4b200_copy_probe(self.handle, ctypes.c_void_p(dst_dev), ctypes.c_void_p(src_dev), nbytes, reps,
+                                          ctypes.byref(ms)), "lz4b200_copy_probe")
+        return 2.0 * nbytes / (ms.value / 1e3) / 1e9
 
     def make_default(self):
         lib().lz4ada_set_device_context(self.handle)

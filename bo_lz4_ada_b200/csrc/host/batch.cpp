@@ -123,6 +123,24 @@ public:
 
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// Host threads one plan may use for its walk.  Eight is plenty for one process; processes (or the threads of the
+// multi-GPU call) that share a box share its cores: LZ4ADA_PLAN_THREADS overrides, LOCAL_WORLD_SIZE (torchrun) divides.
+static thread_local uint32_t g_plan_share = 1;   // set by lz4ada_batch_decompress_multi for its worker threads
+static uint32_t plan_threads()
+{
+	const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+	if (const char *e = getenv("LZ4ADA_PLAN_THREADS")) {
+		const int v = atoi(e);
+		if (v >= 1) return std::min<uint32_t>(uint32_t(v), 64u);
+	}
+	uint32_t share = g_plan_share;
+	if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+		const int v = atoi(e);
+		if (v > 1) share = std::max<uint32_t>(share, uint32_t(v));
+	}
+	return std::max(1u, std::min<uint32_t>(8u, hw / share));
+}
+
 }  // namespace lz4ada
 
 using namespace lz4ada;
@@ -131,11 +149,18 @@ struct lz4ada_batch {
 	lz4b200_ctx *ctx = nullptr;
 	int reservation = LZ4ADA_FOR_ALL;
 	uint64_t src_bytes = 0;
+	uint64_t span_lo = 0, span_hi = 0;   // the part of the source buffer the streams of this batch occupy
 	std::vector<ItemPlan> items;
 	std::vector<FramePlan> frames;
 	std::vector<lz4b200_blk_desc> descs;
 	std::vector<lz4b200_chain> chains;
 	std::vector<lz4b200_frame_blocks> hash_frames;   // frames whose content checksum K3 computes
+	std::vector<uint32_t> k2_idx;                    // stored blocks, copied by K2 (lz4b200_copy_stored) instead of K1
+	std::vector<lz4b200_hash_span> k2_spans;         // ... their payloads, for the block checksums
+	bool k2_checksums = false;
+	uint32_t *d_k2_idx = nullptr, *d_k2_scratch = nullptr;
+	lz4b200_hash_span *d_k2_spans = nullptr;
+	size_t cap_k2 = 0;
 	bool exact_sizing = false;                       // lz4ada_batch_exact_sizing: K5 sizes every block first
 	int64_t heavy_blocks = -1;                       // blocks that take long to decode (K1 kernel choice), -1 = not counted yet
 	const char *k1_name = "";                        // the K1 kernel the last lz4ada_batch_run launched
@@ -174,6 +199,9 @@ struct lz4ada_batch {
 		if (d_status) lz4b200_free(ctx, d_status);
 		if (d_chains) lz4b200_free(ctx, d_chains);
 		if (d_retry_chains) lz4b200_free(ctx, d_retry_chains);
+		if (d_k2_idx) lz4b200_free(ctx, d_k2_idx);
+		if (d_k2_spans) lz4b200_free(ctx, d_k2_spans);
+		if (d_k2_scratch) lz4b200_free(ctx, d_k2_scratch);
 		if (d_hash_frames) lz4b200_free(ctx, d_hash_frames);
 		if (d_digest) lz4b200_free(ctx, d_digest);
 		if (h_status) lz4b200_free_host(ctx, h_status);
@@ -195,6 +223,9 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			if ((*sized_len)[i] != 0xffffffffu) known[b->presize[i]] = (*sized_len)[i];   // 0xffffffff: K5 gave up on it
 	b->chains.clear();
 	b->hash_frames.clear();
+	b->k2_idx.clear();
+	b->k2_spans.clear();
+	b->k2_checksums = false;
 	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of them a
 	// warp: what such a block costs is its serial depth (~100 MB/s per stream whichever kernel walks it -- K1 v4, the
 	// K4 pipeline and the round-based K6 all measure within 10 % of each other), so the shape that
@@ -243,9 +274,19 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 				else run_known = false;
 				const uint64_t hist = off_i;
 				d.hist_avail = hist > 0xfffffffeull ? 0xffffffffu : uint32_t(hist);
-				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO | LZ4B200_BLK_RING_CAP);
+				d.flags &= ~(LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO | LZ4B200_BLK_RING_CAP | LZ4B200_BLK_K2);
 				if (fp.chained) d.flags |= LZ4B200_BLK_CHAINED;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
+				if (!fp.chained && (d.flags & LZ4B200_BLK_STORED) && !(d.flags & LZ4B200_BLK_HASH_ONLY)) {
+					// stored blocks of independent frames: the wide copy K2, not a warp of K1
+					d.flags |= LZ4B200_BLK_K2;
+					b->k2_idx.push_back(fp.first_block + i);
+					lz4b200_hash_span sp;
+					sp.off = d.src_off;
+					sp.len = d.src_len;
+					b->k2_spans.push_back(sp);
+					if (d.flags & LZ4B200_BLK_HAS_CHECKSUM) b->k2_checksums = true;
+				}
 				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max && uint64_t(d.src_len) * 16 >= d.dst_cap) {
 					d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO;
 					lz4b200_chain c;
@@ -266,7 +307,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 								  : 0;
 				b->chains.push_back(c);
 			}
-			if (fp.has_cchk && fp.cchk_seen) {
+			if (fp.has_cchk && fp.cchk_seen && fp.n_blocks) {   // (a frame without blocks has the checksum of no bytes: host)
 				fp.hash_slot = uint32_t(b->hash_frames.size());
 				lz4b200_frame_blocks hb;
 				hb.first_block = fp.first_block;
@@ -310,12 +351,25 @@ int launch_k1(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev, size_t 
 {
 	lz4b200_ctx *ctx = b->ctx;
 	const int saved_tuning = lz4b200_get_tuning(ctx);
-	const bool force_v4 = saved_tuning == 0 && heavy < 16384;
+	const bool force_v4 = saved_tuning == 0 && heavy < 20000;
 	if (force_v4) lz4b200_set_tuning(ctx, 40);
 	b->k1_name = lz4b200_k1_kernel_name(ctx, uint32_t(b1 - b0));
 	const int rc = lz4b200_decode_blocks(ctx, src_dev, dst_dev, uint32_t(b1 - b0), b->d_desc + b0, b->d_status + b0);
 	if (force_v4) lz4b200_set_tuning(ctx, saved_tuning);
 	return rc;
+}
+
+// K2 over the stored blocks among [b0, b1) (the index list is in block order).
+int launch_k2(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev, size_t b0, size_t b1)
+{
+	const auto lo = std::lower_bound(b->k2_idx.begin(), b->k2_idx.end(), uint32_t(b0));
+	const auto hi = std::lower_bound(b->k2_idx.begin(), b->k2_idx.end(), uint32_t(b1));
+	if (lo == hi) return LZ4B200_OK;
+	const size_t k0 = size_t(lo - b->k2_idx.begin()), n = size_t(hi - lo);
+	uint32_t max_len = 0;
+	for (size_t k = k0; k < k0 + n; k++) max_len = std::max(max_len, uint32_t(b->k2_spans[k].len));
+	return lz4b200_copy_stored(b->ctx, src_dev, dst_dev, uint32_t(n), b->d_k2_idx + k0, max_len, b->d_desc, b->d_status,
+				   b->k2_checksums ? b->d_k2_spans + k0 : nullptr, b->k2_checksums ? b->d_k2_scratch + k0 : nullptr);
 }
 
 Raised device_fail(lz4ada_batch *b)
@@ -384,7 +438,9 @@ bool fold_item(lz4ada_batch *b, ItemPlan &it, bool exact, DigestFn digest_of)
 		if (it.error || slow) break;
 		if (fp.has_cchk && fp.cchk_seen) {
 			uint32_t value = 0;
-			if (!digest_of(fp, value)) { slow = true; break; }
+			const uint8_t none = 0;
+			if (fp.n_blocks == 0) value = Xxh32Host::hash(&none, 0);   // XXHash32.Final of nothing, lib/lz4ada.adb:993-1017
+			else if (!digest_of(fp, value)) { slow = true; break; }
 			if (value != fp.cchk_declared) { it.error = err_content_checksum(value, fp.cchk_declared); break; }
 		}
 		if (fp.ended && fp.has_csize && remaining != 0) { it.error = err_content_size_left(remaining); break; }
@@ -443,7 +499,7 @@ Raised run_slow_items(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			FramePlan &fp = b->frames[it.first_frame + f];
 			for (uint32_t i = 0; i < fp.n_blocks; i++) {
 				lz4b200_blk_desc &d = b->descs[fp.first_block + i];
-				d.flags &= ~(LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO);
+				d.flags &= ~(LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO | LZ4B200_BLK_K2);
 				d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_RING_CAP;
 				if (i == 0) d.flags |= LZ4B200_BLK_FIRST_OF_FRAME;
 				d.dst_cap = uint32_t(it.min_buffer);
@@ -546,6 +602,12 @@ int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_by
 	b->reservation = reservation;
 	b->src_bytes = src_bytes;
 	b->items.resize(n_items);
+	b->span_lo = n_items ? ~0ull : 0;
+	for (uint32_t k = 0; k < n_items; k++) {
+		b->span_lo = std::min(b->span_lo, items[k].src_off);
+		b->span_hi = std::max(b->span_hi, items[k].src_off + items[k].src_len);
+	}
+	if (b->span_hi < b->span_lo) b->span_lo = b->span_hi = 0;
 	// A fixed reservation = Init (lib/lz4ada.adb:48-63); Use_First / Single_Frame = Init_With_Header on the whole
 	// stream (:79-125), the call the reference's unlz4ada and its error-case test make
 	const bool with_header = reservation > LZ4ADA_SZ_8_MIB;
@@ -561,8 +623,7 @@ int lz4ada_batch_plan(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t src_by
 		std::vector<FramePlan> frames;
 		std::vector<lz4b200_blk_desc> descs;
 	};
-	const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
-	const uint32_t n_parts = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(8u, hw), n_items / 64u));
+	const uint32_t n_parts = std::max(1u, std::min<uint32_t>(plan_threads(), n_items / 64u));
 	std::vector<Part> parts(n_parts);
 	auto walk_range = [&](uint32_t part) {
 		Part &pt = parts[part];
@@ -759,7 +820,10 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 	}
 	lz4b200_ctx *ctx = b->ctx;
 	const size_t nb = b->descs.size();
-	if (src_host && src_dev && lz4b200_h2d(ctx, src_dev, src_host, b->src_bytes) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+	// (only the bytes the batch's streams occupy: a share of a bigger buffer copies its share)
+	if (src_host && src_dev && b->span_hi > b->span_lo &&
+	    lz4b200_h2d(ctx, src_dev + b->span_lo, src_host + b->span_lo, b->span_hi - b->span_lo) != LZ4B200_OK)
+		return LZ4ADA_DEVICE_ERROR;
 	if (!b->d_desc && nb) {
 		if (lz4b200_alloc(ctx, sizeof(lz4b200_blk_desc) * nb, reinterpret_cast<void **>(&b->d_desc)) != LZ4B200_OK ||
 		    lz4b200_alloc(ctx, sizeof(lz4b200_blk_status) * nb, reinterpret_cast<void **>(&b->d_status)) != LZ4B200_OK ||
@@ -811,6 +875,20 @@ int lz4ada_batch_upload(lz4ada_batch *b, const uint8_t *src_host, uint8_t *src_d
 			    lz4b200_alloc_host(ctx, 8 * nh, reinterpret_cast<void **>(&b->h_digest)) != LZ4B200_OK)
 				return LZ4ADA_DEVICE_ERROR;
 		}
+		const size_t n2 = b->k2_idx.size();
+		if (n2 > b->cap_k2) {
+			if (b->d_k2_idx) { lz4b200_free(ctx, b->d_k2_idx); lz4b200_free(ctx, b->d_k2_spans); lz4b200_free(ctx, b->d_k2_scratch); }
+			b->d_k2_idx = nullptr; b->d_k2_spans = nullptr; b->d_k2_scratch = nullptr;
+			b->cap_k2 = 0;
+			if (lz4b200_alloc(ctx, 4 * n2, reinterpret_cast<void **>(&b->d_k2_idx)) != LZ4B200_OK ||
+			    lz4b200_alloc(ctx, sizeof(lz4b200_hash_span) * n2, reinterpret_cast<void **>(&b->d_k2_spans)) != LZ4B200_OK ||
+			    lz4b200_alloc(ctx, 4 * n2, reinterpret_cast<void **>(&b->d_k2_scratch)) != LZ4B200_OK)
+				return LZ4ADA_DEVICE_ERROR;
+			b->cap_k2 = n2;
+		}
+		if (n2 && (lz4b200_h2d(ctx, b->d_k2_idx, b->k2_idx.data(), 4 * n2) != LZ4B200_OK ||
+			   lz4b200_h2d(ctx, b->d_k2_spans, b->k2_spans.data(), sizeof(lz4b200_hash_span) * n2) != LZ4B200_OK))
+			return LZ4ADA_DEVICE_ERROR;
 		if (lz4b200_h2d(ctx, b->d_desc, b->descs.data(), sizeof(lz4b200_blk_desc) * nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		if (nc && lz4b200_h2d(ctx, b->d_chains, b->chains.data(), sizeof(lz4b200_chain) * nc) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		if (nh && lz4b200_h2d(ctx, b->d_hash_frames, b->hash_frames.data(), sizeof(lz4b200_frame_blocks) * nh) != LZ4B200_OK)
@@ -852,6 +930,7 @@ int lz4ada_batch_run(lz4ada_batch *b, const uint8_t *src_dev, uint8_t *dst_dev)
 			if (b->heavy_blocks < 0) b->heavy_blocks = int64_t(heavy_blocks(b, 0, nb));
 			const int rc1 = launch_k1(b, src_dev, dst_dev, 0, nb, uint64_t(b->heavy_blocks));
 			if (rc1 != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
+			if (launch_k2(b, src_dev, dst_dev, 0, nb) != LZ4B200_OK) return LZ4ADA_DEVICE_ERROR;
 		}
 		lz4b200_event_record(ctx, b->ev[1]);
 		if (nc && lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(nc), b->d_chains, b->d_desc, b->d_status) != LZ4B200_OK)
@@ -937,7 +1016,8 @@ int lz4ada_batch_run_pipelined(lz4ada_batch *b, const uint8_t *src_host, uint8_t
 		if (b1 > b0)
 			bad = bad || lz4b200_memset(ctx, b->d_status + b0, 0xff, sizeof(lz4b200_blk_status) * (b1 - b0)) != LZ4B200_OK;
 		if (b1 > b0)
-			bad = bad || launch_k1(b, src_dev, dst_dev, b0, b1, heavy_blocks(b, b0, b1)) != LZ4B200_OK;
+			bad = bad || launch_k1(b, src_dev, dst_dev, b0, b1, heavy_blocks(b, b0, b1)) != LZ4B200_OK ||
+			      launch_k2(b, src_dev, dst_dev, b0, b1) != LZ4B200_OK;
 		// chains and frame tables index blocks globally, so they get the un-offset arrays
 		if (ncc)
 			bad = bad || lz4b200_decode_linked(ctx, src_dev, dst_dev, uint32_t(ncc), b->d_chains + c0, b->d_desc, b->d_status) != LZ4B200_OK;
@@ -1018,6 +1098,7 @@ struct ScratchPool {
 	lz4b200_frame_blocks *d_hash_frames = nullptr;
 	uint32_t *d_digest = nullptr, *h_digest = nullptr;
 	size_t cap_hash = 0;
+	const char *last_k1 = "";   // K1 kernel of the last call's chunks
 };
 
 static void *pool_make(lz4b200_ctx *ctx)
@@ -1084,8 +1165,9 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 	// spare room of the caller's buffer (up to 32 MiB of it) serves streams that outgrow their region
 	const uint64_t capacity = need + std::min<uint64_t>(dst_bytes - need, 32ull << 20);
 	b->dst_capacity = capacity;
-	if (!pool_reserve(pool, src_bytes, capacity)) return LZ4ADA_DEVICE_ERROR;
-	uint8_t *d_src = pool->d_src, *d_dst = pool->d_dst;
+	if (!pool_reserve(pool, b->span_hi - b->span_lo, capacity)) return LZ4ADA_DEVICE_ERROR;
+	// device scratch holds [span_lo, span_hi) of the source: d_src is where byte 0 of the buffer would be
+	uint8_t *d_src = pool->d_src - b->span_lo, *d_dst = pool->d_dst;
 	// lend pooled table buffers to the batch when they are large enough (cudaMalloc / cudaMallocHost
 	// per call cost ~100 ms, several times the device stage)
 	const size_t nbk = b->descs.size(), nhk = b->hash_frames.size();
@@ -1113,7 +1195,7 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 	if (b->placed && b->descs.size()) {
 		// fast shape: placement is known without touching the device -> pipeline H2D / kernels / D2H
 		rc = lz4ada_batch_upload(b, nullptr, nullptr);   // tables only
-		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 30)));   // ~1 GiB of output each: 16 384 blocks of 64 KiB, enough for the lane-per-block K1
+		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 29)));   // ~512 MiB of output each
 		if (rc == LZ4ADA_OK) rc = lz4ada_batch_run_pipelined(b, src_host, dst_host, d_src, d_dst, chunks);
 	} else {
 		rc = lz4ada_batch_upload(b, src_host, d_src);
@@ -1125,6 +1207,7 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 			if (lz4b200_sync(ctx) != LZ4B200_OK) rc = LZ4ADA_DEVICE_ERROR;
 		}
 	}
+	pool->last_k1 = b->k1_name;
 	if (rc == LZ4ADA_OK && results) lz4ada_batch_results(b, results);
 	if (rc == LZ4ADA_OK && messages && message_stride)
 		for (uint32_t k = 0; k < n_items; k++) {
@@ -1139,6 +1222,109 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 			items[k].dst_cap = b->items[k].dst_cap;
 		}
 	return rc;
+}
+
+const char *lz4ada_last_k1_kernel_name(lz4b200_ctx *ctx)
+{
+	ScratchPool *p = ctx ? pool_for(ctx) : nullptr;
+	return p ? p->last_k1 : "";
+}
+
+int lz4ada_batch_decompress_multi(uint32_t n_ctx, lz4b200_ctx *const *ctxs, const uint8_t *src_host, uint64_t src_bytes,
+				  uint8_t *dst_host, uint64_t dst_bytes, uint32_t n_items, lz4ada_batch_item *items, int reservation,
+				  lz4ada_batch_result *results, char *messages, size_t message_stride)
+{
+	if (n_ctx == 0 || !ctxs || (!items && n_items)) return LZ4ADA_ASSERTION_ERROR;
+	for (uint32_t g = 0; g < n_ctx; g++)
+		if (!ctxs[g]) return LZ4ADA_ASSERTION_ERROR;
+	if (n_ctx == 1)
+		return lz4ada_batch_decompress(ctxs[0], src_host, src_bytes, dst_host, dst_bytes, n_items, items, reservation, results, messages,
+					       message_stride);
+	// ---- deal whole streams to the devices: contiguous runs of the streams in the order given, cut where the running
+	// sum of compressed bytes passes the next n-th of the total (a share's bytes then lie together in the source
+	// buffer, so its H2D copies move its share and nothing else) ----
+	std::vector<std::vector<uint32_t>> share(n_ctx);
+	{
+		uint64_t total = 0;
+		for (uint32_t k = 0; k < n_items; k++) total += items[k].src_len + 1;
+		uint64_t run = 0;
+		for (uint32_t k = 0; k < n_items; k++) {
+			const uint64_t mid = run + (items[k].src_len + 1) / 2;
+			uint32_t g = uint32_t((unsigned __int128)mid * n_ctx / (total ? total : 1));
+			if (g >= n_ctx) g = n_ctx - 1;
+			share[g].push_back(k);
+			run += items[k].src_len + 1;
+		}
+	}
+	// ---- the output room of each device's share: a host-only plan per share (no device needed for that) ----
+	std::vector<uint64_t> need(n_ctx, 0), base(n_ctx, 0);
+	std::vector<std::vector<lz4ada_batch_item>> sub(n_ctx);
+	std::vector<int> rcs(n_ctx, LZ4ADA_OK);
+	auto plan_share = [&](uint32_t g) {
+		g_plan_share = n_ctx;
+		sub[g].resize(share[g].size());
+		for (size_t j = 0; j < share[g].size(); j++) {
+			sub[g][j] = items[share[g][j]];
+			sub[g][j].dst_off = 0;
+			sub[g][j].dst_cap = 0;   // planner-placed inside the share's region
+		}
+		lz4ada_batch *b = nullptr;
+		rcs[g] = lz4ada_batch_plan(nullptr, src_host, src_bytes, uint32_t(sub[g].size()), sub[g].data(), reservation, &b);
+		if (rcs[g] == LZ4ADA_OK) {
+			need[g] = lz4ada_batch_output_bytes(b);
+			lz4ada_batch_free(b);
+		}
+	};
+	{
+		std::vector<std::thread> th;
+		for (uint32_t g = 1; g < n_ctx; g++) th.emplace_back(plan_share, g);
+		plan_share(0);
+		for (auto &t : th) t.join();
+	}
+	for (uint32_t g = 0; g < n_ctx; g++)
+		if (rcs[g] != LZ4ADA_OK) return rcs[g];
+	uint64_t cursor = 0;
+	for (uint32_t g = 0; g < n_ctx; g++) {
+		base[g] = align_up(cursor, 256);
+		cursor = base[g] + need[g];
+	}
+	if (cursor > dst_bytes) return LZ4ADA_ASSERTION_ERROR;
+	const uint64_t spare = (dst_bytes - cursor) / n_ctx;   // room for streams that outgrow their region, split evenly
+	// ---- every device runs its share on a thread of its own ----
+	std::vector<std::vector<lz4ada_batch_result>> res(n_ctx);
+	std::vector<std::vector<char>> msg(n_ctx);
+	auto run_share = [&](uint32_t g) {
+		g_plan_share = n_ctx;
+		res[g].resize(std::max<size_t>(1, share[g].size()));
+		if (messages && message_stride) msg[g].assign(std::max<size_t>(1, share[g].size()) * message_stride, 0);
+		if (share[g].empty()) return;
+		// (the spare room of share g lies behind ALL planned regions, not behind its own: regions are packed)
+		uint8_t *dst_g = dst_host + base[g];
+		uint64_t cap_g = need[g];
+		if (g + 1 == n_ctx) cap_g += spare * n_ctx;   // only the last region can grow in place
+		rcs[g] = lz4ada_batch_decompress(ctxs[g], src_host, src_bytes, dst_g, cap_g, uint32_t(sub[g].size()), sub[g].data(), reservation,
+						 res[g].data(), msg[g].empty() ? nullptr : msg[g].data(), message_stride);
+	};
+	{
+		std::vector<std::thread> th;
+		for (uint32_t g = 1; g < n_ctx; g++) th.emplace_back(run_share, g);
+		run_share(0);
+		for (auto &t : th) t.join();
+	}
+	for (uint32_t g = 0; g < n_ctx; g++)
+		if (rcs[g] != LZ4ADA_OK) return rcs[g];
+	for (uint32_t g = 0; g < n_ctx; g++)
+		for (size_t j = 0; j < share[g].size(); j++) {
+			const uint32_t k = share[g][j];
+			if (results) {
+				results[k] = res[g][j];
+				results[k].dst_off += base[g];
+			}
+			items[k].dst_off = sub[g][j].dst_off + base[g];
+			items[k].dst_cap = sub[g][j].dst_cap;
+			if (messages && message_stride) memcpy(messages + size_t(k) * message_stride, msg[g].data() + j * message_stride, message_stride);
+		}
+	return LZ4ADA_OK;
 }
 
 }  // extern "C"

@@ -109,8 +109,8 @@ public:
 			}
 		}
 		if (!served &&
-		    lz4b200_stream_block(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
-					 buffer + output_pos_, uint32_t(cap), &st) != LZ4B200_OK)
+		    lz4b200_stream_block2(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
+					  buffer + output_pos_, uint32_t(cap), uint32_t(w.m.frame_block_max), &st) != LZ4B200_OK)
 			return device_failure();
 		// Decrease_Data_Size_Remaining (:826-839) fires inside Write_Output, i.e. before any
 		// later check of the same block; the block checksum (:672-676) comes before everything.

@@ -411,7 +411,7 @@ __device__ __forceinline__ void decode_role(const uint8_t *__restrict__ src, uin
 	for (uint32_t bi = 0; bi < cnt; bi++) {
 		const uint32_t b = first + bi;
 		const lz4b200_blk_desc d = desc[b];
-		if (d.flags & LZ4B200_BLK_CHAINED) continue;
+		if (d.flags & LZ4B200_BLK_NOT_K1) continue;
 		const uint8_t *s = src + d.src_off;
 		uint8_t *o = dst + d.dst_off;
 		if (!(d.flags & LZ4B200_BLK_HASH_ONLY) && (d.flags & LZ4B200_BLK_STORED) && d.src_len <= d.dst_cap) {
@@ -560,7 +560,7 @@ __device__ __forceinline__ void hash_role(const uint8_t *__restrict__ src, uint3
 	bool mine = false;
 	if (static_cast<uint32_t>(q) < cnt) {
 		const lz4b200_blk_desc d = desc[first + q];
-		mine = !(d.flags & LZ4B200_BLK_CHAINED);
+		mine = !(d.flags & LZ4B200_BLK_NOT_K1);
 		want = mine && (d.flags & LZ4B200_BLK_HAS_CHECKSUM);
 		if (want) {
 			s = src + d.src_off;

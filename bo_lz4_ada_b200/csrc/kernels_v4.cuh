@@ -648,7 +648,7 @@ __device__ __forceinline__ void decode_group(const uint8_t *__restrict__ src, ui
 	if (static_cast<uint32_t>(lane) < G && first_block + lane < n_blocks) {
 		const lz4b200_blk_desc d = desc[first_block + lane];
 		flags = d.flags;
-		if (!(flags & LZ4B200_BLK_CHAINED)) {
+		if (!(flags & LZ4B200_BLK_NOT_K1)) {
 			state = LS_RUN;
 			s = src + d.src_off;
 			o = dst + d.dst_off;

@@ -272,7 +272,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				const uint32_t b = base + __popc(idle & ((1u << lane) - 1u));
 				if (b < n_blocks) {
 					const lz4b200_blk_desc d = desc[b];
-					if (!(d.flags & LZ4B200_BLK_CHAINED)) {
+					if (!(d.flags & LZ4B200_BLK_NOT_K1)) {
 						blk = b;
 						fresh = true;
 						hflags = d.flags;

@@ -148,7 +148,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 					const uint32_t b = base + __popc(idle & ((1u << lane) - 1u));
 					if (b < n_blocks) {
 						const lz4b200_blk_desc d = desc[b];
-						if (!(d.flags & LZ4B200_BLK_CHAINED)) {
+						if (!(d.flags & LZ4B200_BLK_NOT_K1)) {
 							blk = b;
 							const uint8_t *hs = src + d.src_off;
 							const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(hs) & 15u);
@@ -206,8 +206,12 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		const bool run = state == L_RUN;
 		bool progressed = false, bad = false;
 
+		cp_async_wait<K - 1>();   // the staging slot of the piece pushed K trips ago, and the in-ring chunk requested with it, have landed
+		// the twelve bytes at the parse cursor, requested before the copy side's work so that the parse arithmetic can be
+		// scheduled under it (shared-memory accesses keep their program order; arithmetic does not)
+		const uint32_t va = in_base + (a & (IN_BYTES - 4u));
+		const uint32_t w0 = lds32o<0>(va), w1 = lds32o<4>(va), w2 = lds32o<8>(va), w3 = lds32o<12>(va);
 		// ================= copy side: the piece pushed K trips ago =================
-		cp_async_wait<K - 1>();   // its staging slot (and the in-ring chunk requested with it) has landed
 		{
 			const uint32_t dsc = f_desc[0];
 			const uint32_t nl = (dsc >> 2) & 15u, n = (dsc >> 6) & 31u, info = dsc >> 16;
@@ -266,9 +270,6 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			const uint32_t a_ld = a_req - 16u * __popc(ifl & ((1u << (K - 1)) - 1u));   // chunks below this have landed
 			const bool can = run && !ended && (a_ld >= a_end || a_ld >= a + VIEW) && q - p_fl <= BACKLOG;
 			if (can) {
-				// twelve bytes at the cursor
-				const uint32_t va = in_base + (a & (IN_BYTES - 4u));
-				const uint32_t w0 = lds32o<0>(va), w1 = lds32o<4>(va), w2 = lds32o<8>(va), w3 = lds32o<12>(va);
 				const uint32_t sh = (a & 3u) * 8u;
 				const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
 				// ---- token (only when no sequence is in progress) ----

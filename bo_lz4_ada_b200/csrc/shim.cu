@@ -35,7 +35,7 @@ decode_blocks_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_b
 	const uint32_t b = blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
 	if (b >= n_blocks) return;
 	const lz4b200_blk_desc d = desc[b];
-	if (d.flags & LZ4B200_BLK_CHAINED) return;
+	if (d.flags & LZ4B200_BLK_NOT_K1) return;
 	process_block<false>(src, dst + d.dst_off, d, d.dst_cap, d.hist_avail, status + b, lane);
 }
 
@@ -777,8 +777,15 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 // Streaming content checksum for the single-block path under Update: the XXH32 state lives in
 // device memory between blocks (XXHash32.Update, lib/lz4ada.adb:942-977).
 __global__ void __launch_bounds__(32)
-xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest)
+xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest,
+		    const lz4b200_blk_status *cond = nullptr)
 {
+	// cond: the status of the block decoded just before on the same stream -- hash what it produced, or nothing if
+	// it failed (the host has not seen the status yet: no round trip between decode and hash)
+	if (cond) {
+		if (cond->code != LZ4B200_ST_OK) return;
+		len = cond->out_len;
+	}
 	const int lane = threadIdx.x & 31;
 	const int sub = lane & 3;
 	uint32_t acc = st->acc[sub];
@@ -894,6 +901,66 @@ size_blocks_kernel(const uint8_t *__restrict__ src, uint32_t n_blocks,
 	status[b].aux = 0;
 	status[b].xxh32_computed = 0;
 	status[b].xxh32_declared = 0;
+}
+
+// K2: stored blocks (lib/lz4ada.adb:685-695) as a wide copy -- every warp of the grid takes one 32 KiB tile of one
+// stored block, so a 4 MiB block is spread over 128 warps instead of riding one warp of K1.  The block checksum, a
+// serial XXH32 chain over the payload, runs beside the copy as a quad chain per block (xxh32_spans over the source).
+constexpr uint32_t K2_TILE = 32768;
+
+__global__ void __launch_bounds__(256)
+copy_stored_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_idx, const uint32_t *__restrict__ idx,
+		   const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status, uint32_t tiles_per_block)
+{
+	const int lane = threadIdx.x & 31;
+	const uint64_t w = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t k = static_cast<uint32_t>(w / tiles_per_block), t = static_cast<uint32_t>(w % tiles_per_block);
+	if (k >= n_idx) return;
+	const uint32_t b = idx[k];
+	const lz4b200_blk_desc d = desc[b];
+	const bool fits = d.src_len <= d.dst_cap;
+	if (t == 0 && lane == 0) {
+		// Check_Checksum comes first in the reference (:672-676); verify_stored_kernel overrides this status if it fails
+		status[b].code = fits ? LZ4B200_ST_OK : LZ4B200_ST_OUTPUT_OVERFLOW;
+		status[b].out_len = fits ? d.src_len : 0u;
+		status[b].err_pos = fits ? 0u : d.src_len;
+		status[b].aux = 0;
+		status[b].xxh32_computed = 0;
+		status[b].xxh32_declared = 0;
+	}
+	const uint64_t lo = static_cast<uint64_t>(t) * K2_TILE;
+	if (!fits || lo >= d.src_len) return;
+	const uint32_t n = d.src_len - lo < K2_TILE ? static_cast<uint32_t>(d.src_len - lo) : K2_TILE;
+	warp_copy<true>(dst + d.dst_off + lo, src + d.src_off + lo, n, lane);
+}
+
+// ... and the verdict of the block checksums computed beside it (one thread per stored block with a checksum).
+__global__ void __launch_bounds__(128)
+verify_stored_kernel(const uint8_t *__restrict__ src, uint32_t n_idx, const uint32_t *__restrict__ idx,
+		     const lz4b200_blk_desc *__restrict__ desc, const uint32_t *__restrict__ computed, lz4b200_blk_status *status)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_idx) return;
+	const uint32_t b = idx[k];
+	const lz4b200_blk_desc d = desc[b];
+	if (!(d.flags & LZ4B200_BLK_HAS_CHECKSUM)) return;
+	const uint8_t *t = src + d.src_off + d.src_len;
+	const uint32_t declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+	status[b].xxh32_computed = computed[k];
+	status[b].xxh32_declared = declared;
+	if (computed[k] != declared) {   // lib/lz4ada.adb:702: beats everything else about the block
+		status[b].code = LZ4B200_ST_BLOCK_CHECKSUM;
+		status[b].out_len = 0;
+		status[b].err_pos = 0;
+	}
+}
+
+// The roofline denominator, measured in the same run: a plain 16-byte-per-thread grid-stride copy (read + write).
+__global__ void __launch_bounds__(256)
+copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16)
+{
+	const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+	for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1093,8 +1160,9 @@ static int k1_generation(const lz4b200_ctx *ctx, uint32_t n_blocks)
 	if (g == 0) {
 		// v6 (a lane per block) runs a batch in the time one block takes when the batch fits the resident lanes
 		// (148 SMs x 14 warps x 32), and that time does not shrink with the batch: ~5 ms for 64 KiB text blocks.
-		// v4 (a warp per block) costs ~0.33 us per such block, so it is the faster shape below ~16 000 blocks.
-		g = n_blocks >= 16384u ? 60 : 40;
+		// v4 (a warp per block) costs ~0.37 us per such block, so it is the faster shape below ~20 000 blocks
+		// (measured: 16 384 blocks 6.0 ms v4 / 7.2 ms v6, 32 768 blocks 11.6 / 7.8 ms).
+		g = n_blocks >= 20000u ? 60 : 40;
 	}
 	return g;
 }
@@ -1184,6 +1252,29 @@ int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms)
 	CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
 	return LZ4B200_OK;
 }
+
+int lz4b200_copy_probe(lz4b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes, int reps, float *best_ms)
+{
+	if (!ctx || !dst_dev || !src_dev || !best_ms || reps < 1 || bytes < 16) return LZ4B200_ERR_ARG;
+	const size_t n16 = bytes / 16;
+	const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+	float best = 0;
+	for (int r = 0; r < reps + 1; r++) {   // (the first pass warms up)
+		CK(cudaEventRecord(ctx->ev0, ctx->stream));
+		copy_probe_kernel<<<sms * 16, 256, 0, ctx->stream>>>(static_cast<const uint4 *>(src_dev), static_cast<uint4 *>(dst_dev), n16);
+		ctx->launches++;
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		CK(cudaEventSynchronize(ctx->ev1));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		if (r > 0 && (best == 0 || ms < best)) best = ms;
+	}
+	*best_ms = best;
+	return LZ4B200_OK;
+}
+
+int lz4b200_device_of(const lz4b200_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 int lz4b200_event_create(lz4b200_ctx *ctx, void **event)
 {
@@ -1326,6 +1417,30 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 	}
 	ctx->launches++;
 	CK(cudaGetLastError());
+	return LZ4B200_OK;
+}
+
+int lz4b200_copy_stored(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t n_idx, const uint32_t *idx,
+			uint32_t max_len, const lz4b200_blk_desc *desc, lz4b200_blk_status *status,
+			const lz4b200_hash_span *spans, uint32_t *scratch)
+{
+	if (!ctx || (n_idx && !idx)) return LZ4B200_ERR_ARG;
+	if (n_idx == 0) return LZ4B200_OK;
+	const uint32_t tiles = max_len ? (max_len + K2_TILE - 1) / K2_TILE : 1;
+	const uint64_t warps = static_cast<uint64_t>(n_idx) * tiles;
+	const uint64_t grid = (warps + 7) / 8;
+	if (grid > 0x7fffffffull) return LZ4B200_ERR_ARG;
+	copy_stored_kernel<<<static_cast<uint32_t>(grid), 256, 0, ctx->stream>>>(src, dst, n_idx, idx, desc, status, tiles);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	if (spans && scratch) {
+		// block checksums of the stored payloads: one quad chain per block, then the comparison
+		const int rc = lz4b200_xxh32_spans(ctx, src, n_idx, spans, scratch);
+		if (rc != LZ4B200_OK) return rc;
+		verify_stored_kernel<<<(n_idx + 127) / 128, 128, 0, ctx->stream>>>(src, n_idx, idx, desc, scratch, status);
+		ctx->launches++;
+		CK(cudaGetLastError());
+	}
 	return LZ4B200_OK;
 }
 
@@ -1490,9 +1605,9 @@ int lz4b200_stream_reset(lz4b200_stream *s)
 	return LZ4B200_OK;
 }
 
-int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len, uint32_t flags,
-			 int hash_content, uint8_t *host_dst, uint32_t dst_cap,
-			 lz4b200_blk_status *status)
+int lz4b200_stream_block2(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len, uint32_t flags,
+			  int hash_content, uint8_t *host_dst, uint32_t dst_cap, uint32_t expect_out,
+			  lz4b200_blk_status *status)
 {
 	if (!s || !status) return LZ4B200_ERR_ARG;
 	lz4b200_ctx *ctx = s->ctx;
@@ -1518,30 +1633,49 @@ int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t sr
 	CK(cudaMemcpyAsync(s->d_meta + META_DESC, hd, sizeof *hd, cudaMemcpyHostToDevice, ctx->stream));
 	// the history in front of the cursor is final: matches may read backwards across the
 	// block boundary (ALLOW_HIST)
+	lz4b200_blk_status *d_st = reinterpret_cast<lz4b200_blk_status *>(s->d_meta + META_STATUS);
 	stream_block_kernel<<<1, 32, 0, ctx->stream>>>(
-		s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC),
-		reinterpret_cast<lz4b200_blk_status *>(s->d_meta + META_STATUS));
+		s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC), d_st);
 	ctx->launches++;
 	CK(cudaGetLastError());
+	// One synchronisation per block when the caller can say how much a well-formed block produces at most (the
+	// frame's block maximum, up to 256 KiB): the content hash reads the block's status on the device, and that many
+	// bytes come back with the status.  A block that produced more (the reference bounds it by the caller's Buffer
+	// only) fetches the rest afterwards.
+	const uint32_t spec = expect_out && expect_out <= (256u << 10) ? (expect_out < dst_cap ? expect_out : dst_cap) : 0u;
+	if (spec && hash_content) {
+		xxh32_stream_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH), s->d_win + s->cursor, 0,
+							       nullptr, d_st);
+		ctx->launches++;
+		CK(cudaGetLastError());
+	}
 	CK(cudaMemcpyAsync(s->h_meta + META_STATUS, s->d_meta + META_STATUS, sizeof(lz4b200_blk_status),
 			   cudaMemcpyDeviceToHost, ctx->stream));
+	if (spec) CK(cudaMemcpyAsync(host_dst, s->d_win + s->cursor, spec, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	*status = *reinterpret_cast<lz4b200_blk_status *>(s->h_meta + META_STATUS);
 	if (status->code != LZ4B200_ST_OK) return LZ4B200_OK;
 	const uint32_t n = status->out_len;
-	if (n > 0) {
-		if (hash_content) {
+	if (n > spec) {
+		if (hash_content && !spec) {
 			xxh32_stream_kernel<<<1, 32, 0, ctx->stream>>>(
 				reinterpret_cast<XxhState *>(s->d_meta + META_XXH), s->d_win + s->cursor, n, nullptr);
 			ctx->launches++;
 			CK(cudaGetLastError());
 		}
-		CK(cudaMemcpyAsync(host_dst, s->d_win + s->cursor, n, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(host_dst + spec, s->d_win + s->cursor + spec, n - spec, cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
 	}
 	s->cursor += n;
 	s->frame_pos += n;
 	return LZ4B200_OK;
+}
+
+int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len, uint32_t flags,
+			 int hash_content, uint8_t *host_dst, uint32_t dst_cap,
+			 lz4b200_blk_status *status)
+{
+	return lz4b200_stream_block2(s, host_src, src_len, flags, hash_content, host_dst, dst_cap, 0, status);
 }
 
 int lz4b200_stream_adopt(lz4b200_stream *s, const uint8_t *dev_bytes, uint32_t n, int hash_content)

@@ -70,6 +70,8 @@ typedef struct lz4b200_blk_desc {
                                        * (Min_Buffer_Size = reservation block size + 64 KiB + 8, lib/lz4ada.adb:54);
                                        * the block may produce what is left of it behind the ring cursor
                                        * (:678-680) -- the only bound the reference puts on a block's output */
+#define LZ4B200_BLK_K2           128u /* a stored block the host has routed to lz4b200_copy_stored; K1 skips it */
+#define LZ4B200_BLK_NOT_K1 (LZ4B200_BLK_CHAINED | LZ4B200_BLK_K2)
 #define LZ4B200_BLK_SOLO          32u /* chain of one block taken from an independent frame (big blocks get a
                                        * whole CTA): its exact path keeps independent-block semantics */
 
@@ -185,6 +187,12 @@ int lz4b200_sync(lz4b200_ctx *ctx);
 int lz4b200_timer_start(lz4b200_ctx *ctx);
 int lz4b200_timer_stop(lz4b200_ctx *ctx, float *elapsed_ms);   /* synchronises */
 
+/* The roofline denominator measured in place: a plain grid-stride copy of `bytes` from src_dev to dst_dev (read +
+ * write = 2 * bytes of HBM traffic), `reps` timed passes after one warm-up; best_ms = the fastest pass. */
+int lz4b200_copy_probe(lz4b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes, int reps, float *best_ms);
+/* CUDA device ordinal of the context. */
+int lz4b200_device_of(const lz4b200_ctx *ctx);
+
 /* CUDA events on the context stream, for per-kernel timing without libcudart on the caller's
  * side.  elapsed is valid once the stream has been synchronised past `stop`. */
 int lz4b200_event_create(lz4b200_ctx *ctx, void **event);
@@ -199,6 +207,14 @@ int lz4b200_event_elapsed(lz4b200_ctx *ctx, void *start, void *stop, float *elap
 int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst,
 		uint32_t n_blocks, const lz4b200_blk_desc *desc,
 		lz4b200_blk_status *status);
+
+/* K2: stored (uncompressed) blocks as a wide copy (lib/lz4ada.adb:685-695): block idx[k] of the table for k <
+ * n_idx, every block cut into 32 KiB tiles with a warp each (max_len = the longest of them).  spans / scratch (n_idx
+ * entries each, or NULL when no block carries a checksum): spans[k] = the payload of block idx[k] in src; its XXH32
+ * is computed as a chain of its own beside the copy (Check_Checksum, :698-707) and compared with the trailer. */
+int lz4b200_copy_stored(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t n_idx, const uint32_t *idx,
+		uint32_t max_len, const lz4b200_blk_desc *desc, lz4b200_blk_status *status,
+		const lz4b200_hash_span *spans, uint32_t *scratch);
 
 /* K4: chains -- blocks in order by one warp, chains in parallel; the running output
  * position of the chain places every block, so matches may reach back across block
@@ -245,6 +261,13 @@ int lz4b200_stream_reset(lz4b200_stream *s);
 int lz4b200_stream_block(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len,
 		uint32_t flags, int hash_content, uint8_t *host_dst, uint32_t dst_cap,
 		lz4b200_blk_status *status);
+/* The same with a hint: expect_out = what a well-formed block of this frame produces at most (the frame's block
+ * maximum).  Up to 256 KiB the call then needs ONE synchronisation instead of two: the content hash reads the block's
+ * status on the device and expect_out bytes come back together with the status (bytes of host_dst behind the block's
+ * output and below expect_out are overwritten -- free space of the caller's Buffer).  0 = no hint. */
+int lz4b200_stream_block2(lz4b200_stream *s, const uint8_t *host_src, uint32_t src_len,
+		uint32_t flags, int hash_content, uint8_t *host_dst, uint32_t dst_cap,
+		uint32_t expect_out, lz4b200_blk_status *status);
 /* XXH32 of every byte produced since the last reset (XXHash32.Final, :993-1017). */
 int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32);
 /* Read-ahead support: n decoded bytes that already sit in device memory
@@ -430,6 +453,18 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 		uint8_t *dst_host, uint64_t dst_bytes, uint32_t n_items,
 		lz4ada_batch_item *items, int reservation, lz4ada_batch_result *results,
 		char *messages, size_t message_stride);
+
+/* Name of the K1 kernel the last lz4ada_batch_decompress on this context launched for its chunks. */
+const char *lz4ada_last_k1_kernel_name(lz4b200_ctx *ctx);
+
+/* The same call over several GPUs of one box: whole streams are dealt to the contexts (one per
+ * GPU) in contiguous runs balanced by compressed size -- a content-checksummed frame is never split, nothing is exchanged between devices
+ * -- and every context runs its share on a host thread of its own (plan, H2D, kernels, D2H), all reading from and
+ * writing into the caller's two host buffers.  Results, messages and the placement written back to items[] are in
+ * the order the streams were given.  n_ctx = 1 is lz4ada_batch_decompress. */
+int lz4ada_batch_decompress_multi(uint32_t n_ctx, lz4b200_ctx *const *ctxs, const uint8_t *src_host, uint64_t src_bytes,
+		uint8_t *dst_host, uint64_t dst_bytes, uint32_t n_items, lz4ada_batch_item *items, int reservation,
+		lz4ada_batch_result *results, char *messages, size_t message_stride);
 
 #ifdef __cplusplus
 }

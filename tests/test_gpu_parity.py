@@ -261,6 +261,16 @@ def test_batch_all_good_vectors(ctx):
         _check_output(stem, out)
 
 
+@pytest.mark.parametrize("stem", ["empty", "emptycraft", "skippable", "z1", "t2"])
+def test_batch_of_one_tiny_stream(ctx, stem):
+    """A batch that is nothing but one frame without blocks (or one skippable frame, or one stored byte): no kernel has
+    anything to do for some of them, the outcome still comes from the fold (content checksum of no bytes included)."""
+    (exc, out, eof, msg), = lz.batch_decompress(ctx, [_read(stem + ".lz4")])
+    assert exc == "OK", msg
+    assert eof != "No"
+    _check_output(stem, out)
+
+
 def test_batch_error_vectors_match_oracle(ctx, oracle):
     """Every .err vector through the batch path (Init(For_All) semantics) = the oracle's
     Init(For_All)+Update loop: same exception, same text, same bytes before the error."""
@@ -1027,23 +1037,31 @@ def test_pipelined_host_path(ctx, oracle):
         assert bytes(out2[results[k].dst_off:results[k].dst_off + results[k].out_len]) == oout
 
 
-def test_cli_unlz4ada_b200(ctx):
-    """The stdin -> stdout tool (counterpart of tool_unlz4ada_simple; test_run.sh's check: rv = 0 and
-    sha256(out) == sha256(.bin)) on every good vector, and a non-zero exit with the library's
-    exception text on an error vector."""
+@pytest.mark.parametrize("mode", [[], ["--update"]])
+def test_cli_unlz4ada_b200(ctx, mode):
+    """The stdin -> stdout tool (counterpart of tool_unlz4ada / tool_unlz4ada_simple; test_run.sh's check: rv = 0 and
+    sha256(out) == sha256(.bin)) on every good vector -- through the batched device entry point (default) and through
+    the Update loop (--update) -- and a non-zero exit with the library's exception text on an error vector."""
     import subprocess
     exe = os.path.join(ROOT, "tools", "unlz4ada_b200")
     if not os.path.exists(exe):
         pytest.skip("tools/unlz4ada_b200 not built")
     for stem in GOOD:
-        p = subprocess.run([exe], input=_read(stem + ".lz4"), capture_output=True)
+        p = subprocess.run([exe] + mode, input=_read(stem + ".lz4"), capture_output=True)
         assert p.returncode == 0, (stem, p.stderr)
         _check_output(stem, p.stdout)
-    p = subprocess.run([exe], input=_read("corruptionoffset0.err"), capture_output=True)
+    p = subprocess.run([exe] + mode, input=_read("corruptionoffset0.err"), capture_output=True)
     assert p.returncode == 1
     assert p.stderr.decode().strip() == "raised LZ4ADA.DATA_CORRUPTION : Corrupted Block: Offset = 0 detected."
-    p = subprocess.run([exe], input=_read("t100k.lz4")[:5000], capture_output=True)
+    p = subprocess.run([exe] + mode, input=_read("t100k.lz4")[:5000], capture_output=True)
     assert p.returncode == 2
+    # bytes decoded before an error are written first (corruptedcntchcksm: the whole content, then the checksum error)
+    p = subprocess.run([exe] + mode, input=_read("corruptedcntchcksm.err"), capture_output=True)
+    assert p.returncode == 1 and "content checksum" in p.stderr.decode() and len(p.stdout) > 0
+    # -v: an I/O-inclusive figure on stderr
+    p = subprocess.run([exe] + mode + ["-v"], input=_read("t1111k.lz4"), capture_output=True)
+    assert p.returncode == 0 and "MB/s decompressed" in p.stderr.decode()
+    _check_output("t1111k", p.stdout)
 
 
 def test_pipelined_chains_repeatable(ctx):
@@ -1068,3 +1086,88 @@ def test_pipelined_chains_repeatable(ctx):
         for plain, (exc, out, eof, msg) in zip(plains, lz.batch_decompress(ctx, streams)):
             assert exc == "OK", msg
             assert out == plain, rep
+
+
+@pytest.mark.parametrize("chain,solo", [("k6", "1"), ("k6", "0"), ("warp", "1"), ("pipe", "1")])
+def test_chain_kernel_variants(chain, solo):
+    """The chain kernels are chosen once per process from the environment: K6 (pointer-doubling parser + round-based
+    copier on a shared-memory window), the K4 pipeline and the one-warp kernel, with and without big independent blocks
+    placed as chains of one.  Each in a process of its own: good vectors, synthetic frames (linked, stored blocks
+    inside linked frames, long literal runs, zero pages) and corrupted streams against the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+import bo_lz4_ada_b200 as lz
+import oracle_binding
+import test_gpu_parity as T
+from tools import corpus
+oracle = oracle_binding.load()
+ctx = lz.DeviceContext(0); ctx.make_default()
+streams = [T._read(s + ".lz4") for s in T.GOOD]
+for stem, (exc, out, eof, msg) in zip(T.GOOD, lz.batch_decompress(ctx, streams)):
+    assert exc == "OK", (stem, msg)
+    T._check_output(stem, out)
+cases = T._synthetic_frames()
+for (name, frame, plain), (exc, out, eof, msg) in zip(cases, lz.batch_decompress(ctx, [c[1] for c in cases])):
+    assert exc == "OK" and out == plain, (name, msg)
+text = corpus.text_like(3 << 20, seed=41)
+big = [corpus.build_frame(text[i * 1000:i * 1000 + 2500000], 7, i %% 2 == 0, True) for i in range(4)]
+big += [corpus.build_frame(text[:1500000] + bytes(300000) + corpus.random_bytes(200000, seed=3) + text[1500000:2000000], 6, True, True, independent=False)]
+for k, (exc, out, eof, msg) in enumerate(lz.batch_decompress(ctx, big)):
+    oexc, oout, oeof, omsg = oracle.decode_stream(big[k], chunk=0, out_cap=4 << 20)
+    assert (exc, out) == (oexc, oout) and exc == "OK", (k, msg)
+rng = np.random.default_rng(5)
+mix = text[:200000] + bytes(5000) + corpus.random_bytes(3000, seed=1) + text[200000:450000]
+bad = T._mutations(corpus.build_frame(mix, 4, True, True, True, independent=False), rng, 60) + T._mutations(big[1][:400000] + big[1][400000:], rng, 12)
+for k, (data, (exc, out, eof, msg)) in enumerate(zip(bad, lz.batch_decompress(ctx, bad))):
+    oexc, oout, oeof, omsg = oracle.decode_stream(data, chunk=0, out_cap=4 << 20)
+    assert (exc, msg, out) == (oexc, omsg, oout), (k, exc, msg, oexc, omsg)
+print("variant ok")
+''' % (ROOT, ROOT)
+    env = dict(os.environ, LZ4B200_CHAIN_KERNEL=chain, LZ4B200_SOLO=solo)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and "variant ok" in p.stdout, p.stderr[-2000:]
+
+
+def test_batch_decompress_multi(oracle):
+    """lz4ada_batch_decompress_multi: whole streams dealt to several device contexts in contiguous runs, every context
+    on a host thread of its own, one source and one destination buffer (two and three contexts on the device this box
+    has): outcomes, messages and bytes are the single-context call's."""
+    import ctypes
+    c = corpus.build_corpus(20 << 20, 1 << 20, 4, kinds=("text", "rle", "random"), keep_plain=True)
+    text = corpus.text_like(200000, seed=78)
+    extra = [corpus.build_frame(text, 4, False, True, block_size=30000), corpus.build_frame(text, 5, True, True, independent=False),
+             _read("corruptedcntchcksm.err"), _read("cntblkszoverflow.err"), _read("t300k.lz4"), _read("z9m.lz4")]
+    streams = [bytes(c["src"][o:o + n]) for o, n in c["items"]] + extra
+    src = b"".join(streams)
+    offs, pos = [], 0
+    for st in streams:
+        offs.append((pos, len(st)))
+        pos += len(st)
+    expect = [oracle.decode_stream(st, chunk=0, out_cap=10 << 20) for st in streams]
+    cap = sum(len(e[1]) for e in expect) + (32 << 20)
+    for n_ctx in (1, 2, 3):
+        ctxs = [lz.DeviceContext(0) for _ in range(n_ctx)]
+        handles = (ctypes.c_void_p * n_ctx)(*[cx.handle for cx in ctxs])
+        items = (lz.BatchItem * len(offs))()
+        for k, (o, n) in enumerate(offs):
+            items[k].src_off, items[k].src_len = o, n
+        results = (lz.BatchResult * len(offs))()
+        msgs = ctypes.create_string_buffer(256 * len(offs))
+        out = bytearray(cap)
+        addr = (ctypes.c_uint8 * len(out)).from_buffer(out)
+        rc = lz.lib().lz4ada_batch_decompress_multi(n_ctx, handles, src, len(src), addr, cap, len(offs), items,
+                                                    lz.RESERVATIONS["For_All"], results, msgs, 256)
+        assert rc == 0, (n_ctx, rc)
+        for k, (oexc, oout, oeof, omsg) in enumerate(expect):
+            assert lz.EXC_NAMES[results[k].exception] == oexc, (n_ctx, k)
+            assert msgs.raw[256 * k:256 * (k + 1)].split(b"\0")[0].decode() == omsg, (n_ctx, k)
+            assert bytes(out[results[k].dst_off:results[k].dst_off + results[k].out_len]) == oout, (n_ctx, k)
+        # regions of different streams never overlap
+        spans = sorted((results[k].dst_off, results[k].dst_off + results[k].out_len) for k in range(len(offs)) if results[k].out_len)
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), n_ctx
+        for cx in ctxs:
+            cx.close()
