@@ -7,6 +7,7 @@
 //                                 (lz4ada_batch_decompress: block table on the host, H2D, kernels, D2H) -- SURVEY.md 8f-1
 //   unlz4ada_b200 --update [-v]   the drop-in streaming API instead: Init + Update on 8 MiB reads, one block per call
 //                                 (tool_unlz4ada_simple/unlz4ada_simple.adb:23-36 with a bigger read)
+//   --file F --repeat N           read F instead of stdin, N passes in one process (the first pays for the CUDA context)
 //   -v                            timing on stderr, I/O included: bytes in / out, seconds from the first read to the last
 //                                 write, decompressed MB/s; and the same without I/O
 //   exit 0: ok      exit 1: LZ4Ada exception (text on stderr, like GNAT's unhandled-exception line; the bytes decoded
@@ -24,7 +25,7 @@ static double now()
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int run_update(bool verbose)
+static int run_update(bool verbose, FILE *in_f, FILE *out_f)
 {
 	const double t0 = now();
 	int min_buffer_size = 0;
@@ -36,7 +37,7 @@ static int run_update(bool verbose)
 	double t_lib = 0;
 	for (;;) {
 		// big reads: the library decodes ahead when it sees whole blocks behind the current one in its Input
-		const size_t got = fread(input.data(), 1, input.size(), stdin);
+		const size_t got = fread(input.data(), 1, input.size(), in_f);
 		if (got == 0) break;
 		total_in += got;
 		size_t pos = 0;
@@ -47,12 +48,12 @@ static int run_update(bool verbose)
 						     min_buffer_size, &first, &last);
 			t_lib += now() - a;
 			if (rc != LZ4ADA_OK) {
-				fflush(stdout);
+				if (out_f) fflush(out_f);
 				fprintf(stderr, "%s\n", lz4ada_exception_message(ctx));
 				return 1;
 			}
 			if (last >= first) {
-				fwrite(output.data() + first, 1, static_cast<size_t>(last - first + 1), stdout);
+				if (out_f) fwrite(output.data() + first, 1, static_cast<size_t>(last - first + 1), out_f);
 				total_out += static_cast<size_t>(last - first + 1);
 			}
 			pos += static_cast<size_t>(consumed);
@@ -60,7 +61,7 @@ static int run_update(bool verbose)
 	}
 	const int eof = lz4ada_is_end_of_frame(ctx);
 	lz4ada_free(ctx);
-	fflush(stdout);
+	if (out_f) fflush(out_f);
 	if (verbose) {
 		const double dt = now() - t0;
 		fprintf(stderr, "update: %zu bytes in, %zu bytes out, %.3f s with I/O = %.1f MB/s decompressed; %.3f s inside Update = %.1f MB/s\n",
@@ -73,14 +74,14 @@ static int run_update(bool verbose)
 	return 0;
 }
 
-static int run_batch(bool verbose)
+static int run_batch(bool verbose, FILE *in_f, FILE *out_f)
 {
 	const double t0 = now();
 	std::vector<uint8_t> in;
 	{
 		std::vector<uint8_t> chunk(8u << 20);
 		for (;;) {
-			const size_t got = fread(chunk.data(), 1, chunk.size(), stdin);
+			const size_t got = fread(chunk.data(), 1, chunk.size(), in_f);
 			if (got == 0) break;
 			in.insert(in.end(), chunk.begin(), chunk.begin() + got);
 		}
@@ -108,8 +109,8 @@ static int run_batch(bool verbose)
 		fprintf(stderr, "raised LZ4ADA.DEVICE_ERROR : lz4ada_batch_decompress failed (rc=%d): no CUDA device or driver. This library has no CPU decode path.\n", rc);
 		return 1;
 	}
-	if (res.out_len) fwrite(out.data() + res.dst_off, 1, res.out_len, stdout);
-	fflush(stdout);
+	if (res.out_len && out_f) fwrite(out.data() + res.dst_off, 1, res.out_len, out_f);
+	if (out_f) fflush(out_f);
 	if (verbose) {
 		const double dt = now() - t0;
 		fprintf(stderr, "batch: %zu bytes in, %llu bytes out, %.3f s with I/O = %.1f MB/s decompressed; %.3f s in the batch call (table + H2D + kernels + D2H) = %.1f MB/s\n",
@@ -129,13 +130,28 @@ static int run_batch(bool verbose)
 int main(int argc, char **argv)
 {
 	bool update = false, verbose = false;
+	const char *file = nullptr;
+	int repeat = 1;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--update")) update = true;
 		else if (!strcmp(argv[i], "-v")) verbose = true;
+		else if (!strcmp(argv[i], "--file") && i + 1 < argc) file = argv[++i];
+		else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
 		else {
-			fprintf(stderr, "usage: unlz4ada_b200 [--update] [-v] < in.lz4 > out\n");
+			fprintf(stderr, "usage: unlz4ada_b200 [--update] [-v] [--file in.lz4 [--repeat N]] < in.lz4 > out\n");
 			return 3;
 		}
 	}
-	return update ? run_update(verbose) : run_batch(verbose);
+	if (!file) return update ? run_update(verbose, stdin, stdout) : run_batch(verbose, stdin, stdout);
+	// --file F --repeat N: decode F N times in this process (the first pass pays for the CUDA context, the device
+	// and pinned buffers; later passes show the path itself); only the last pass writes its output
+	int rc = 0;
+	for (int r = 0; r < repeat && rc == 0; r++) {
+		FILE *f = fopen(file, "rb");
+		if (!f) { perror(file); return 3; }
+		FILE *out_f = r + 1 == repeat ? stdout : nullptr;
+		rc = update ? run_update(verbose, f, out_f) : run_batch(verbose, f, out_f);
+		fclose(f);
+	}
+	return rc;
 }
