@@ -1171,3 +1171,52 @@ def test_batch_decompress_multi(oracle):
         assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), n_ctx
         for cx in ctxs:
             cx.close()
+
+
+@pytest.mark.parametrize("g", [-1, 8, 41, 50, 60, 61])
+def test_guard_bands(ctx, g):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted the plain way: the output buffer is
+    painted, streams are placed by the CALLER with gaps between them and guard bands at both ends, and after the run
+    every byte outside the bytes a stream produced must still carry the paint -- for each K1 generation, with stored
+    blocks (K2), linked frames (K4), misaligned placements and streams that end in an error."""
+    text = corpus.text_like(400000, seed=61)
+    rle = corpus.rle_like(300000, seed=62)
+    rnd = corpus.random_bytes(150000, seed=63)
+    plains = [text, rle, rnd, text[:70001], text[1000:200000] + rle[:100000] + rnd[:70000], text[:65536 * 3]]
+    streams = [corpus.build_frame(plains[0], 4, True, True), corpus.build_frame(plains[1], 4, False, True),
+               corpus.build_frame(plains[2], 4, True, True), corpus.build_frame(plains[3], 5, True, True),
+               corpus.build_frame(plains[4], 4, True, True, independent=False), corpus.build_frame(plains[5], 4, True, True)]
+    streams.append(_read("backrefoverflow.err"))
+    plains.append(None)
+    src = b"".join(streams)
+    guard = 4096
+    items, pos, spos = [], guard + 3, 0
+    for st, pl in zip(streams, plains):
+        cap = (len(pl) if pl is not None else 65536) + 17
+        items.append((spos, len(st), pos, cap))
+        spos += len(st)
+        pos += cap + 129 + (pos % 7)        # odd gaps: placements are not 16-byte aligned
+    total = pos + guard
+    ctx.set_tuning(g)
+    try:
+        b = lz.Batch(ctx, src, items)
+        d_src, d_dst = ctx.alloc(len(src) + 64), ctx.alloc(total + 64)
+        lz.lib().lz4b200_memset(ctx.handle, d_dst, 0xA5, total + 64)
+        b.upload(d_src)
+        b.run(d_src, d_dst)
+        res = b.results()
+        out = np.frombuffer(ctx.d2h(d_dst, total), dtype=np.uint8).copy()
+        for (so, sl, do, dc), pl, r in zip(items, plains, res):
+            if pl is not None:
+                assert r["exception"] == "OK" and r["dst_off"] == do, r
+                assert bytes(out[do:do + r["out_len"]]) == pl
+            # erase what the stream legitimately produced (a stream that ends in an error may have written the bytes of
+            # its failing block that precede the error: they are inside its region and are not handed out)
+            out[do:do + (r["out_len"] if pl is not None else dc)] = 0xA5
+        stray = np.flatnonzero(out != 0xA5)
+        assert stray.size == 0, (g, stray[:8], len(stray))
+        b.close()
+        ctx.free(d_src)
+        ctx.free(d_dst)
+    finally:
+        ctx.set_tuning(0)
