@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--skip-configs", action="store_true", help="only the headline workload")
     ap.add_argument("--config2-gib", type=float, default=4.0, help="configs[2]: decompressed GiB per GPU (weak)")
     ap.add_argument("--strong", action="store_true", help="configs[2] as the 16 GiB corpus split over the ranks")
+    ap.add_argument("--corpus-rank", type=int, default=-1, help="seed the corpora as this rank would (diagnostics)")
     ap.add_argument("--k1-group", type=int, default=0,
                     help="K1 tuning (include/lz4b200.h): 0 auto, 60 v6, 50 v5, 40 v4, 64 v3, 1..16 v2, -1 v1")
     return ap.parse_args()
@@ -244,6 +245,7 @@ class Device:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.seed_rank = args.corpus_rank if args.corpus_rank >= 0 else self.rank
         if not torch.cuda.is_available():
             sys.exit("bench.py: no CUDA device -- this arm has no CPU fallback")
         torch.cuda.set_device(self.local)
@@ -257,6 +259,15 @@ class Device:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def gather(self, value):
+        """value of every rank, in rank order"""
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return [float(t.item())]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
 
     def reduce(self, value, op):
         t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda")
@@ -302,9 +313,10 @@ def device_resident(dev, c, steps, warmup):
         kms.append(batch.kernel_ms())
     e1.record()
     dev.barrier()
-    ms = dev.reduce(e0.elapsed_time(e1), "MAX") / steps
+    per_rank = [x / steps for x in dev.gather(e0.elapsed_time(e1))]
+    ms = max(per_rank)
     total_plain = dev.reduce(plain_bytes, "SUM")
-    out = {"ms_per_step": ms, "plain_bytes_all_ranks": total_plain, "plain_bytes": plain_bytes, "n_src": n_src,
+    out = {"ms_per_step": ms, "ms_per_step_per_rank": per_rank, "plain_bytes_all_ranks": total_plain, "plain_bytes": plain_bytes, "n_src": n_src,
            "out_bytes": out_bytes, "launches": dev.ctx.launch_count() - launches0, "traffic": batch.traffic(),
            "k1_name": batch.k1_kernel_name() or dev.ctx.k1_kernel_name(batch.block_count), "blocks": int(batch.block_count),
            "kernel_ms": {k: float(np.mean([m[k] for m in kms])) for k in kms[0]}, "h_src": h_src, "d_src": d_src, "d_dst": d_dst}
@@ -341,7 +353,7 @@ def secondary_configs(dev, args, peak, peak_src):
     def entry(name, c, scaling):
         r = device_resident(dev, c, steps, warm)
         e = {"name": name, "value": r["plain_bytes_all_ranks"] / (r["ms_per_step"] / 1e3) / 1e9, "unit": "GB/s",
-             "ms_per_step": r["ms_per_step"], "scaling": scaling, "streams_per_gpu": len(c["items"]), "blocks_per_gpu": r["blocks"],
+             "ms_per_step": r["ms_per_step"], "ms_per_step_per_rank": r["ms_per_step_per_rank"], "scaling": scaling, "streams_per_gpu": len(c["items"]), "blocks_per_gpu": r["blocks"],
              "plain_bytes_per_gpu": r["plain_bytes"], "compressed_bytes_per_gpu": r["n_src"], "bit_exact": True,
              "kernel_ms": r["kernel_ms"], "k1_kernel": r["k1_name"], "roofline": roofline_of(r, peak, peak_src)}
         del r
@@ -353,14 +365,14 @@ def secondary_configs(dev, args, peak, peak_src):
     gib = 16.0 / dev.world if args.strong else args.config2_gib
     n = max(3, int(gib * GIB) // (4 << 20))
     c = corpus.build_corpus(n * (4 << 20), 4 << 20, 7, kinds=("rle", "text", "random"), block_checksum=False,
-                            seed=4321 + 1000003 * dev.rank, workers=max(4, (os.cpu_count() or 8) // max(1, dev.world)))
+                            seed=4321 + 1000003 * dev.seed_rank, workers=max(4, (os.cpu_count() or 8) // max(1, dev.world)))
     out.append(entry("configs[2]: %.3g GiB per GPU of the 4 MiB-block corpus (thirds RLE / text / random, one-block frames)%s"
                      % (gib, ", the 16 GiB corpus split over %d ranks" % dev.world if args.strong else ""), c,
                      "strong" if args.strong else "weak"))
     del c
     # configs[3]: legacy frames (8 MiB blocks), concatenated modern frames, skippable frames: 1024 streams
-    text = corpus.text_like(6 << 20, seed=5 + dev.rank)
-    rle = corpus.rle_like(2 << 20, seed=6 + dev.rank)
+    text = corpus.text_like(6 << 20, seed=5 + dev.seed_rank)
+    rle = corpus.rle_like(2 << 20, seed=6 + dev.seed_rank)
 
     def mixed_stream(i):
         a = text[(i * 4099) % (5 << 20):][:200000 + (i % 7) * 30000]
@@ -418,7 +430,7 @@ def copy_ceiling(dev, h_src, h_dst, n_src, n_dst, steps=3):
 def run_ours(args):
     dev = Device(args)
     torch, lz, world, rank = dev.torch, dev.lz, dev.world, dev.rank
-    c = make_corpus(args, rank)
+    c = make_corpus(args, dev.seed_rank)
     peak, peak_src = peaks()
 
     sampler = ClockSampler(dev.local)
@@ -511,6 +523,7 @@ def run_ours(args):
                          % (n_src / 1e9, plain_bytes / 1e9),
                    "corpus_build_s": round(c["build_s"], 1)},
         "clocks": sampler.summary(),
+        "ms_per_step_per_rank": r["ms_per_step_per_rank"],
         "gpu_launches": int(r["launches"]),
         "kernel_ms": r["kernel_ms"],
         "roofline": {"bound": "hbm", "kernel": k1_name + " (K1)", "achieved": achieved, "peak": peak,

@@ -139,6 +139,7 @@ _SIGNATURES = {
     "lz4b200_set_tuning": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_get_tuning": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
+    "lz4b200_k1_fallbacks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     "lz4b200_use_lane": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_sync_all": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -151,6 +152,8 @@ _SIGNATURES = {
     "lz4b200_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "lz4b200_copy_stored": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
+                                           ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_copy_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_float)]),
     "lz4b200_device_of": (ctypes.c_int, [ctypes.c_void_p]),
@@ -310,6 +313,12 @@ class DeviceContext:
     def k1_kernel_name(self, n_blocks):
         """Which K1 kernel lz4b200_decode_blocks launches for n_blocks under the current tuning."""
         return lib().lz4b200_k1_kernel_name(self.handle, int(n_blocks)).decode()
+
+    def k1_fallbacks(self):
+        """(blocks the last v6 launch handed to the exact routine, of those by the safety net)"""
+        a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        lib().lz4b200_k1_fallbacks(self.handle, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
 
     def alloc(self, nbytes):
         p = ctypes.c_void_p()

@@ -24,7 +24,7 @@
 //   out ring  the lane's last 256 / 512 bytes, word w of lane L at word w * 32 + L (bank = lane: conflict-free)
 //
 // Block checksums (Check_Checksum, :698-707) are folded in per lane as the chunks arrive, as in v5.  Anything the
-// fast path does not take -- stored blocks, length extensions of 270 bytes and more, every error -- goes to
+// fast path does not take -- stored blocks, length fields longer than the in ring shows, every error -- goes to
 // process_block (exact semantics of :716-904) for the whole block.
 #pragma once
 
@@ -268,26 +268,49 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		// ================= parse side: one piece (Decompress_Sequence, lib/lz4ada.adb:737-777) =================
 		{
 			const uint32_t a_ld = a_req - 16u * __popc(ifl & ((1u << (K - 1)) - 1u));   // chunks below this have landed
-			const bool can = run && !ended && (a_ld >= a_end || a_ld >= a + VIEW) && q - p_fl <= BACKLOG;
+			bool can = run && !ended && (a_ld >= a_end || a_ld >= a + VIEW) && q - p_fl <= BACKLOG;
+			const uint32_t sh = (a & 3u) * 8u;
+			const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+			const bool fresh = (rem_l | rem_m | need_off) == 0;   // the cursor stands on a token
+			// ---- rare: a length whose first extension byte is 255 (runs of 270 literals / matches of 274 bytes and more,
+			// Decompress_Sequence's length loops, :741-747 and :773-777).  The bytes behind the first are summed here, out of
+			// the in ring, in a loop of their own; the trip then consumes the whole length field and no payload.  A match
+			// length is only taken this way by a trip that starts at the offset (a trip that finds one behind its literals
+			// stops in front of the offset).  Fields longer than the ring can show go to the exact routine.
+			const bool long_l = fresh && a + 1 < a_end && (v0 & 0xfff0u) == 0xfff0u;
+			const bool long_m = need_off != 0 && rem_l == 0 && mln == 15u && a + 2 < a_end && ((v0 >> 16) & 255u) == 255u;
+			uint32_t x_sum = 0, x_cnt = 0;
+			bool x_over = false;
+			if (can && (long_l || long_m)) {
+				uint32_t pos = a + (long_l ? 2u : 3u);
+				for (;;) {
+					if (pos >= a_end || pos - a > 64u) { x_over = true; break; }
+					if (pos >= a_ld) { can = false; break; }   // not landed yet: this lane sits the trip out
+					const uint32_t b = (lds32(in_base + (pos & (IN_BYTES - 4u))) >> ((pos & 3u) * 8u)) & 255u;
+					x_sum += b;
+					x_cnt++;
+					pos++;
+					if (b != 255u) break;
+				}
+			}
 			if (can) {
-				const uint32_t sh = (a & 3u) * 8u;
-				const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
 				// ---- token (only when no sequence is in progress) ----
-				const bool fresh = (rem_l | rem_m | need_off) == 0;
 				const bool end0 = fresh && a >= a_end;   // the block ends behind a match, or is empty
 				const bool tok = fresh && !end0;
 				const uint32_t tk = v0 & 255u, e1 = (v0 >> 8) & 255u;
 				const bool ext_l = tok && tk >= 0xf0u;
-				uint32_t o = tok ? (ext_l ? 2u : 1u) : 0u;   // bytes of the view consumed
+				uint32_t o = tok ? (ext_l ? 2u + x_cnt : 1u) : 0u;   // bytes of the view consumed
 				if (tok) {
-					rem_l = (tk >> 4) + (ext_l ? e1 : 0u);
+					rem_l = (tk >> 4) + (ext_l ? e1 + x_sum : 0u);
 					mln = tk & 15u;
 					need_off = 1;
 				}
-				// (long runs -- an extension byte of 255 -- are the exact routine's business)
-				bad = (ext_l && (e1 == 255u || a + 1 >= a_end)) || (tok && rem_l > a_end - a - o);
+				uint32_t why = 0;   // (statistics only)
+				if ((ext_l && a + 1 >= a_end) || (long_l && x_over)) why |= 1u;
+				if (tok && rem_l > a_end - a - o) why |= 2u;
+				bad = why != 0;
 				// ---- literals of this piece: they travel in the descriptor ----
-				const uint32_t lim = tok ? 7u : LIT_PIECE;
+				const uint32_t lim = long_l ? 0u : tok ? 7u : LIT_PIECE;
 				const uint32_t nl = rem_l < lim ? rem_l : lim;
 				n_d0 = __funnelshift_r(v0, v1, o * 8u);
 				n_d1 = __funnelshift_r(v1, v2, o * 8u);
@@ -297,21 +320,24 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				const bool do_off = need_off != 0 && rem_l == 0 && !end0;
 				const uint32_t ao = a + o;
 				const bool fin_lit = do_off && ao >= a_end;   // final literal-only sequence (:752-764)
-				const bool has_m = do_off && !fin_lit;
 				const uint32_t wi = o >> 2;   // 32 bits at view byte o (o <= 9)
 				const uint32_t xa = wi == 0 ? v0 : wi == 1 ? v1 : v2, xb = wi == 0 ? v1 : wi == 1 ? v2 : 0u;
 				const uint32_t X = __funnelshift_r(xa, xb, (o & 3u) * 8u);
 				const uint32_t off = X & 0xffffu, e2 = (X >> 16) & 255u;
 				const bool ext_m = mln == 15u;
+				const bool defer = ext_m && e2 == 255u && !long_m && ao + 2 < a_end;   // the next trip starts at the offset
+				const bool has_m = do_off && !fin_lit && !defer;
 				if (has_m) {
-					rem_m = mln + 4u + (ext_m ? e2 : 0u);
+					rem_m = mln + 4u + (ext_m ? e2 + x_sum : 0u);
 					dist = off;
-					o += ext_m ? 3u : 2u;
+					o += ext_m ? 3u + x_cnt : 2u;
 					need_off = 0;
 				}
-				bad = bad || (fin_lit && mln != 0) ||
-				      (has_m && (ao + 2 > a_end || off == 0 || off > q + nl - p_start ||   // :766-772, :864-874
-						 (ext_m && (e2 == 255u || ao + 2 >= a_end))));
+				if (fin_lit && mln != 0) why |= 4u;
+				if (has_m && (ao + 2 > a_end || off == 0)) why |= 8u;                       // :766-772
+				if (has_m && off > q + nl - p_start) why |= 16u;                            // :864-874
+				if (has_m && ext_m && (ao + 2 >= a_end || (long_m && x_over))) why |= 32u;
+				bad = why != 0;
 				if (end0 || fin_lit) {
 					ended = true;
 					need_off = 0;
@@ -338,7 +364,12 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 				}
 				rem_m -= n;
 				if (dist < ML_PIECE && n == dist) dist <<= 1;   // the pattern has doubled
-				bad = bad || nl + n > p_cap - q;   // the exact routine reports the overflow
+				if (nl + n > p_cap - q) { why |= 64u; bad = true; }   // the exact routine reports the overflow
+				if (bad) {
+					counter[3] = blk;
+					counter[4] = why;
+					counter[5] = a - a_beg;
+				}
 				q += nl + n;
 				n_desc = kind | (nl << 2) | (n << 6) | (info << 16);
 				progressed = true;
@@ -346,6 +377,7 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 		}
 		if (bad) {
 			// hand the block to the exact routine (it decodes from the start and reports); forget what is queued
+			atomicAdd(counter + 1, 1u);   // (statistics: lz4b200_k1_fallbacks)
 			state = L_EXACT;
 			n_desc = 0;
 #pragma unroll
@@ -470,7 +502,10 @@ __device__ __forceinline__ void decode_lanes(const uint8_t *__restrict__ src, ui
 			const bool moving = progressed || state != L_RUN || (ifl & ((1u << K) - 1u)) != 0;
 			idle_trips = __any_sync(FULL_MASK, moving) ? 0u : idle_trips + 1u;
 			if (idle_trips > 4096u) {
-				if (state == L_RUN) state = L_EXACT;
+				if (state == L_RUN) {
+					atomicAdd(counter + 2, 1u);
+					state = L_EXACT;
+				}
 				idle_trips = 0;
 			}
 		}

@@ -1153,6 +1153,21 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp)
 
 int lz4b200_get_tuning(const lz4b200_ctx *ctx) { return ctx ? ctx->blocks_per_warp : 0; }
 
+int lz4b200_k1_fallbacks(lz4b200_ctx *ctx, uint32_t *to_exact, uint32_t *by_safety_net)
+{
+	if (!ctx || !ctx->d_counter) return LZ4B200_ERR_ARG;
+	uint32_t h[6] = {0, 0, 0, 0, 0, 0};
+	int li = 0;
+	for (int i = 0; i < 4; i++)
+		if (ctx->lanes[i] == ctx->stream) li = i;
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpy(h, ctx->d_counter + 16 * li, sizeof h, cudaMemcpyDeviceToHost));
+	if (to_exact) *to_exact = h[1];
+	if (by_safety_net) *by_safety_net = h[2];
+	if (getenv("LZ4B200_V6_DEBUG") && h[1]) fprintf(stderr, "[lz4b200 v6] %u blocks to the exact routine; last: block %u, reason bits 0x%x, input position %u\n", h[1], h[3], h[4], h[5]);
+	return LZ4B200_OK;
+}
+
 // the auto rule of lz4b200_decode_blocks, in one place
 static int k1_generation(const lz4b200_ctx *ctx, uint32_t n_blocks)
 {
@@ -1330,7 +1345,7 @@ int lz4b200_decode_blocks(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 		for (int i = 0; i < 4; i++)
 			if (ctx->lanes[i] == ctx->stream) li = i;
 		uint32_t *counter = ctx->d_counter + 16 * li;
-		CK(cudaMemsetAsync(counter, 0, 4, ctx->stream));
+		CK(cudaMemsetAsync(counter, 0, 24, ctx->stream));   // [0] block queue head, [1] blocks handed to the exact routine, [2] of those by the safety net, [3..5] the last of them: block, reason bits, input position
 		const uint32_t sms = static_cast<uint32_t>(ctx->sm_count > 0 ? ctx->sm_count : 148);
 		// One CTA per SM.  A block is one lane's work from start to end, so a batch that fits the resident lanes runs
 		// as long as one block does: give each SM just the warps that hold the batch (the fewer share an SM, the

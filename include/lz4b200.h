@@ -161,6 +161,10 @@ int lz4b200_set_tuning(lz4b200_ctx *ctx, int blocks_per_warp);
 
 int lz4b200_get_tuning(const lz4b200_ctx *ctx);
 
+/* Statistics of the last lane-per-block K1 launch (v6) on the context's current lane: how many blocks its fast path
+ * handed to the exact routine, and how many of those the idle-trip safety net sent there.  Synchronises the lane. */
+int lz4b200_k1_fallbacks(lz4b200_ctx *ctx, uint32_t *to_exact, uint32_t *by_safety_net);
+
 /* Name of the kernel lz4b200_decode_blocks would launch for n_blocks under the current tuning
  * (for logs and benchmark records). */
 const char *lz4b200_k1_kernel_name(const lz4b200_ctx *ctx, uint32_t n_blocks);

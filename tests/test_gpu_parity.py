@@ -891,6 +891,36 @@ def test_k1_v3_shapes_direct(ctx, oracle, g):
         assert out == exp, (g, len(blk))
 
 
+@pytest.mark.parametrize("g", [60, 61])
+def test_k1_v6_long_length_fields_stay_in_the_lane(ctx, g):
+    """Length fields with extension bytes of 255 (literal runs >= 270, matches >= 274; Decompress_Sequence's length
+    loops, lib/lz4ada.adb:741-747 / :773-777) are decoded by the v6 lane itself -- lz4b200_k1_fallbacks stays at 0 --
+    at the block start, behind a match, with the long match directly behind the token and behind literals (the trip
+    that stops in front of the offset); a field of more than 64 extension bytes goes to the exact routine and is
+    still right."""
+    rng = np.random.default_rng(99)
+    noise = lambda n: bytes(rng.integers(0, 256, n, dtype=np.uint8))
+    blocks = []
+    for ll in (270, 271, 524, 525, 526, 779, 1000, 4000, 16000):
+        blocks.append(_raw_block([(noise(ll), 5, 9), (b"ab", 2, 30)], b"end"))            # at the block start
+        blocks.append(_raw_block([(b"qrstu", 5, 9), (noise(ll), 100, 20)], noise(ll)))     # behind a match; and final
+    for ml in (273, 274, 275, 528, 529, 530, 783, 1039, 5000, 16000):
+        for lead in (1, 3, 6, 7, 8, 14, 15, 16, 40):
+            blocks.append(_raw_block([(noise(lead), lead, ml), (b"", 300 if lead + ml > 300 else 1, ml)], b"xy"))
+    plain = blocks
+    expect = [_py_decode(b) for b in plain]
+    cap = max(len(e) for e in expect)
+    for (code, out_len, out), exp in zip(_run_blocks_direct(ctx, plain, cap, g), expect):
+        assert code == 0 and out == exp, (g, code, out_len, len(exp))
+    assert ctx.k1_fallbacks() == (0, 0)
+    # beyond what a lane follows: 80 extension bytes
+    far = [_raw_block([(noise(15 + 255 * 80 + 7), 9, 12)], b"z"), _raw_block([(b"abc", 3, 19 + 255 * 80 + 3)], b"z")]
+    expect = [_py_decode(b) for b in far]
+    for (code, out_len, out), exp in zip(_run_blocks_direct(ctx, far, 24000, g), expect):
+        assert code == 0 and out == exp, (g, code, out_len, len(exp))
+    assert ctx.k1_fallbacks() == (2, 0)
+
+
 def test_k1_v3_many_blocks_property(ctx):
     """4096 text blocks of 64 KiB (eight per CTA, every hash quad busy) through the batch path:
     output identical to the plain data and the device content checksums agree with the frames'."""
