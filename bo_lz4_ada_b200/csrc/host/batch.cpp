@@ -226,14 +226,15 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 	b->k2_idx.clear();
 	b->k2_spans.clear();
 	b->k2_checksums = false;
-	// Big independent blocks (block maximum >= 1 MiB, ~10^5 sequences in series) stay in K1, which gives each of them a
-	// warp: what such a block costs is its serial depth (~100 MB/s per stream whichever kernel walks it -- K1 v4, the
-	// K4 pipeline and the round-based K6 all measure within 10 % of each other), so the shape that
-	// keeps the most streams resident wins: 2 960 warps of K1 against 148 - 296 CTAs of a chain kernel.
-	// LZ4B200_SOLO=1 turns the chain-per-block placement on (A/B switch; not RLE-like blocks only).
+	// Big independent blocks (block maximum >= 1 MiB and >= 64 KiB of compressed bytes: ~10^5 sequences in series) are
+	// placed as chains of one block: K1 gives such a block one warp, which walks it at ~100 MB/s whatever the kernel
+	// generation, the chain kernel K7 gives it a CTA that parses and copies it without a serial walk (kernels_k7.cuh;
+	// 2.2x per stream measured on text).  Highly compressible big blocks (zero pages, RLE: a few KiB of compressed
+	// bytes, some giant matches) stay in K1, whose warp-wide copies are what they need.  LZ4B200_SOLO=0 turns the
+	// placement off (A/B switch).
 	static const bool solo_on = [] {
 		const char *e = getenv("LZ4B200_SOLO");
-		return e && e[0] == '1';
+		return !(e && e[0] == '0');
 	}();
 	uint64_t cursor = 0;
 	for (ItemPlan &it : b->items) {
@@ -253,7 +254,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			FramePlan &fp = b->frames[it.first_frame + f];
 			fp.dst_off = pos;
 			fp.chained = !fp.independent && fp.n_blocks > 1;
-			// a big block is ~10^5 sequences in series: give it the pipelined chain kernel (one CTA)
+			// a big block is ~10^5 sequences in series: give it the chain kernel (one CTA)
 			fp.solo = solo_on && !fp.chained && fp.block_max >= (1u << 20);
 			fp.hash_slot = 0xffffffffu;
 			// blocks sit one block-maximum apart (the frame format has no per-block decompressed size) -- unless K5
@@ -287,7 +288,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 					b->k2_spans.push_back(sp);
 					if (d.flags & LZ4B200_BLK_HAS_CHECKSUM) b->k2_checksums = true;
 				}
-				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536 && d.dst_cap == fp.block_max && uint64_t(d.src_len) * 16 >= d.dst_cap) {
+				if (fp.solo && !(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536) {
 					d.flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO;
 					lz4b200_chain c;
 					c.first_block = fp.first_block + i;

@@ -727,6 +727,9 @@ __device__ __forceinline__ void copier_role(Shared &sh, uint32_t ring, uint8_t *
 				reseed(w, C0 + total, lane);
 			} else {
 				okay = copy_batch_rounds(w, src + soff, inr, sh.in_mis[sl], out + fbase, C0, ostart, total, cap_abs, sh.sd[sl], cnt, lane, tile);
+				// (timing aid, LZ4B200_K6_DBG = 2 r: every batch is copied 1 + r times -- the same bytes again)
+				for (uint32_t rep = 0; rep < (dbg >> 1) && okay; rep++)
+					copy_batch_rounds(w, src + soff, inr, sh.in_mis[sl], out + fbase, C0, ostart, total, cap_abs, sh.sd[sl], cnt, lane, tile);
 			}
 			if (okay) produced_to = C0 + total;
 			else flush_tail(w, C0, lane);   // everything before the failing batch is final output

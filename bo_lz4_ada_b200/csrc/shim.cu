@@ -16,6 +16,7 @@
 #include "kernels_v5.cuh"
 #include "kernels_v6.cuh"
 #include "kernels_k6.cuh"
+#include "kernels_k7.cuh"
 #include "lz4b200.h"
 
 using namespace lz4b200;
@@ -672,6 +673,53 @@ decode_chain_k6_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n
 	if (warp == 0) chain_exact_tail(sh.fail_block, ch, src, out, desc, status, lane);
 }
 
+// K7: one CTA per chain, no serial walk (kernels_k7.cuh): a speculative parse by every thread, then the output built
+// 16 KiB at a time in shared memory with match bytes as pointers that are resolved by pointer jumping.
+constexpr uint32_t K7_SMEM = sizeof(k7::Shared);
+__global__ void __launch_bounds__(k7::T, k7::T == 512 ? 2 : 3)
+decode_chain_k7_kernel(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t n_chains,
+		       const lz4b200_chain *__restrict__ chains, const lz4b200_blk_desc *__restrict__ desc,
+		       lz4b200_blk_status *status)
+{
+	extern __shared__ __align__(16) uint8_t k7_smem[];
+	k7::Shared &sh = *reinterpret_cast<k7::Shared *>(k7_smem);
+	const uint32_t c = blockIdx.x;
+	if (c >= n_chains) return;
+	const lz4b200_chain ch = chains[c];
+	uint8_t *out = dst + ch.dst_off;
+	const uint32_t fb = k7::run_chain(sh, ch, src, out, desc, status);
+	if (threadIdx.x < 32) chain_exact_tail(fb, ch, src, out, desc, status, threadIdx.x & 31);
+}
+
+// ... and in front of it: the block checksums of every chained block (Check_Checksum, lib/lz4ada.adb:698-707), a quad
+// per block and all blocks of the launch at once instead of one serial hash after the other inside the chain's CTA.
+// Results go to the status entries (xxh32_computed / xxh32_declared), where the chain kernel reads them.
+__global__ void __launch_bounds__(128)
+chain_block_hashes_kernel(const uint8_t *__restrict__ src, uint32_t n_chains, const lz4b200_chain *__restrict__ chains,
+			  const lz4b200_blk_desc *__restrict__ desc, lz4b200_blk_status *status)
+{
+	const uint32_t c = blockIdx.x;
+	if (c >= n_chains) return;
+	const lz4b200_chain ch = chains[c];
+	const int lane = threadIdx.x & 31;
+	const uint32_t quad = threadIdx.x >> 2;
+	for (uint32_t i0 = 0; i0 < ch.n_blocks; i0 += 32) {
+		const uint32_t i = i0 + quad;
+		const bool have = i < ch.n_blocks;
+		const uint32_t b = ch.first_block + (have ? i : 0u);
+		const lz4b200_blk_desc d = desc[b];
+		const bool want = have && (d.flags & LZ4B200_BLK_HAS_CHECKSUM) && !(d.flags & LZ4B200_BLK_HASH_ONLY);
+		if (!__any_sync(FULL_MASK, want)) continue;
+		const uint8_t *s = src + d.src_off;
+		const uint32_t h = quad_xxh32_prologue(s, want ? d.src_len : 0u, lane);
+		if (want && (lane & 3) == 0) {
+			const uint8_t *t = s + d.src_len;
+			status[b].xxh32_computed = h;
+			status[b].xxh32_declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+		}
+	}
+}
+
 // One block against a device-resident history window (single-block path under Update).
 // The K1 v4 block decoder (parallel parse, shared-memory ring) with the window in front of the cursor as
 // history; the exact routine takes over for anything unusual.
@@ -714,6 +762,43 @@ stream_block_kernel(const uint8_t *__restrict__ src, uint8_t *win, const lz4b200
 		__syncwarp();
 	}
 	process_block<true>(src, win + d.dst_off, d, d.dst_cap, d.hist_avail, status, lane);
+}
+
+// ... and a big block under Update: the same history window, decoded by a whole CTA with the chain kernel's machinery
+// (kernels_k7.cuh) instead of one warp; the exact routine takes over for anything unusual, as above.
+__global__ void __launch_bounds__(k7::T, k7::T == 512 ? 2 : 3)
+stream_block_k7_kernel(const uint8_t *__restrict__ src, uint8_t *win, const lz4b200_blk_desc *desc, lz4b200_blk_status *status)
+{
+	extern __shared__ __align__(16) uint8_t k7_smem[];
+	k7::Shared &sh = *reinterpret_cast<k7::Shared *>(k7_smem);
+	const int lane = threadIdx.x & 31;
+	const lz4b200_blk_desc d = *desc;
+	uint32_t fb = 0;
+	if (!(d.flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_HASH_ONLY)) && d.dst_off < 0x70000000ull && d.dst_cap < 0x08000000u) {
+		if ((d.flags & LZ4B200_BLK_HAS_CHECKSUM) && threadIdx.x < 32) {   // verified before any decoding, lib/lz4ada.adb:672-676
+			const uint8_t *s = src + d.src_off;
+			const uint8_t *t = s + d.src_len;
+			uint32_t computed = quad_xxh32_prologue(s, lane < 4 ? d.src_len : 0u, lane);
+			computed = __shfl_sync(FULL_MASK, computed, 0);
+			if (lane == 0) {
+				status->xxh32_computed = computed;
+				status->xxh32_declared = ld_u8<true>(t) | (ld_u8<true>(t + 1) << 8) | (ld_u8<true>(t + 2) << 16) | (ld_u8<true>(t + 3) << 24);
+			}
+		}
+		__syncthreads();
+		// history the reference would accept: the frame's bytes in front of the cursor, at most what the window holds
+		const uint32_t before = static_cast<uint32_t>(d.dst_off);
+		const uint32_t hist = d.hist_avail < before ? d.hist_avail : before;
+		lz4b200_chain ch;
+		ch.first_block = 0;
+		ch.n_blocks = 1;
+		ch.dst_off = 0;
+		ch.dst_cap = static_cast<uint64_t>(hist) + d.dst_cap;
+		fb = k7::run_chain(sh, ch, src, win + d.dst_off - hist, desc, status, hist);
+		if (fb == 0xffffffffu) return;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) process_block<true>(src, win + d.dst_off, d, d.dst_cap, d.hist_avail, status, lane);
 }
 
 // K3: one XXH32 chain per byte range, eight ranges per warp (a quad each).
@@ -1062,6 +1147,8 @@ int lz4b200_create(int device, void *stream, lz4b200_ctx **out)
 		cudaFuncSetAttribute(decode_blocks_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v4::WARPS * sizeof(v4::WarpMem)));
 		cudaFuncSetAttribute(decode_chain_k6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(K6_SMEM));
+		cudaFuncSetAttribute(decode_chain_k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(K7_SMEM));
+		cudaFuncSetAttribute(stream_block_k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(K7_SMEM));
 		cudaFuncSetAttribute(decode_blocks_v6_kernel<64, V6A_K, V6A_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				     int(v6::Layout<64, V6A_K>::smem_bytes(V6A_WARPS)));
 		cudaFuncSetAttribute(decode_blocks_v6_kernel<128, V6B_K, V6B_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1465,14 +1552,35 @@ int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 {
 	if (!ctx) return LZ4B200_ERR_ARG;
 	if (n_chains == 0) return LZ4B200_OK;
-	// LZ4B200_CHAIN_KERNEL=warp selects the one-warp-per-chain kernel (A/B comparisons, tests)
-	// The default is the K4 pipeline (one parser warp, seven gated copier warps).  LZ4B200_CHAIN_KERNEL=k6 selects K6
-	// (pointer-doubling parser + round-based copier on a shared-memory window: same speed per stream, kept for A/B and
-	// as the base of a many-warps-per-stream kernel), =warp the one-warp-per-chain kernel
+	// The default is K7 (one CTA per chain: speculative parse + pointer jumping, kernels_k7.cuh).  For A/B comparisons and
+	// tests LZ4B200_CHAIN_KERNEL selects the earlier generations: pipe = K4 (one parser warp, seven gated copier warps),
+	// k6 = K6 (pointer-doubling parser + round-based copier on a shared-memory window), warp = one warp per chain
 	static const int which = [] {
 		const char *e = getenv("LZ4B200_CHAIN_KERNEL");
-		return e && e[0] == 'w' ? 1 : e && e[0] == 'k' ? 0 : 2;
+		return e && e[0] == 'w' ? 1 : e && e[0] == 'k' && e[1] == '6' ? 0 : e && e[0] == 'p' ? 2 : 3;
 	}();
+	if (which == 3) {
+		chain_block_hashes_kernel<<<n_chains, 128, 0, ctx->stream>>>(src, n_chains, chains, desc, status);
+		decode_chain_k7_kernel<<<n_chains, k7::T, K7_SMEM, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
+		ctx->launches += 2;
+		CK(cudaGetLastError());
+		static const bool dbg7 = getenv("LZ4B200_K7_DEBUG") != nullptr;
+		if (dbg7) {
+			uint32_t h[8] = {};
+			CK(cudaStreamSynchronize(ctx->stream));
+			CK(cudaMemcpyFromSymbol(h, k7::g_stats, sizeof h));
+			fprintf(stderr, "[lz4b200 k7] blocks finished %u, given up %u (last: reason %u, block %u, input position %u)\n", h[0], h[1], h[2], h[3], h[4]);
+			memset(h, 0, sizeof h);
+			CK(cudaMemcpyToSymbol(k7::g_stats, h, sizeof h));
+			unsigned long long q[16] = {};
+			CK(cudaMemcpyFromSymbol(q, k7::g_prof, sizeof q));
+			fprintf(stderr, "[lz4b200 k7] steps %llu, parse iterations %llu, resolve calls %llu rounds %llu; kilocycles (thread 0, summed over CTAs): stage %llu parse %llu place %llu windows %llu (init %llu resolve %llu flush %llu)\n",
+				q[0], q[1], q[2], q[3], q[4] >> 10, q[5] >> 10, q[6] >> 10, q[7] >> 10, q[10] >> 10, q[8] >> 10, q[9] >> 10);
+			memset(q, 0, sizeof q);
+			CK(cudaMemcpyToSymbol(k7::g_prof, q, sizeof q));
+		}
+		return LZ4B200_OK;
+	}
 	if (which == 1) {
 		const uint32_t grid = (n_chains + K1_WARPS - 1) / K1_WARPS;
 		decode_linked_kernel<<<grid, K1_WARPS * 32, 0, ctx->stream>>>(src, dst, n_chains, chains, desc, status);
@@ -1649,8 +1757,17 @@ int lz4b200_stream_block2(lz4b200_stream *s, const uint8_t *host_src, uint32_t s
 	// the history in front of the cursor is final: matches may read backwards across the
 	// block boundary (ALLOW_HIST)
 	lz4b200_blk_status *d_st = reinterpret_cast<lz4b200_blk_status *>(s->d_meta + META_STATUS);
-	stream_block_kernel<<<1, 32, 0, ctx->stream>>>(
-		s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC), d_st);
+	// a block of some size gets a CTA (the chain kernel's parallel parse and pointer jumping), a small one a warp
+	static const bool big_on = [] {
+		const char *e = getenv("LZ4B200_STREAM_K7");
+		return !(e && e[0] == '0');
+	}();
+	if (big_on && src_len >= 16384u && !(flags & (LZ4B200_BLK_STORED | LZ4B200_BLK_HASH_ONLY)))
+		stream_block_k7_kernel<<<1, k7::T, K7_SMEM, ctx->stream>>>(
+			s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC), d_st);
+	else
+		stream_block_kernel<<<1, 32, 0, ctx->stream>>>(
+			s->d_src, s->d_win, reinterpret_cast<const lz4b200_blk_desc *>(s->d_meta + META_DESC), d_st);
 	ctx->launches++;
 	CK(cudaGetLastError());
 	// One synchronisation per block when the caller can say how much a well-formed block produces at most (the

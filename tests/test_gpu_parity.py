@@ -1118,7 +1118,7 @@ def test_pipelined_chains_repeatable(ctx):
             assert out == plain, rep
 
 
-@pytest.mark.parametrize("chain,solo", [("k6", "1"), ("k6", "0"), ("warp", "1"), ("pipe", "1")])
+@pytest.mark.parametrize("chain,solo", [("k7", "1"), ("k7", "0"), ("k6", "1"), ("k6", "0"), ("warp", "1"), ("pipe", "1")])
 def test_chain_kernel_variants(chain, solo):
     """The chain kernels are chosen once per process from the environment: K6 (pointer-doubling parser + round-based
     copier on a shared-memory window), the K4 pipeline and the one-warp kernel, with and without big independent blocks

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-block-checksum", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--linked", action="store_true", help="block-dependent frames (chains: K4 / K6)")
     args = ap.parse_args()
     import torch
     import bo_lz4_ada_b200 as lz
@@ -32,7 +33,7 @@ def main():
 
     code = {"64k": 4, "256k": 5, "1m": 6, "4m": 7}[args.block]
     c = corpus.build_corpus(args.size_mib << 20, int(args.frame_mib * (1 << 20)), code, kinds=tuple(args.kinds.split(",")),
-                            block_checksum=not args.no_block_checksum, seed=args.seed)
+                            block_checksum=not args.no_block_checksum, seed=args.seed, independent=not args.linked)
     src_np = np.frombuffer(c["src"], dtype=np.uint8)
     n_src = len(src_np)
     stream = torch.cuda.current_stream()
@@ -57,6 +58,8 @@ def main():
         k1 = float(np.mean([m["k1_decode_blocks"] for m in ms[1:]]))
         k4 = float(np.mean([m.get("k4_decode_linked", 0.0) for m in ms[1:]]))
         k3 = float(np.mean([m["k3_xxh32_frames"] for m in ms[1:]]))
+        if bad:
+            print("bad streams: %d of %d; first: %s" % (len(bad), len(res), [(i, r["exception"], r["message"][:100]) for i, r in enumerate(res) if r["exception"] != "OK"][:3]), file=sys.stderr)
         print(json.dumps({"tuning": t, "fallbacks": ctx.k1_fallbacks() if t in (60, 61) else None, "kernel": batch.k1_kernel_name(), "blocks": int(batch.block_count), "plain_bytes": plain, "ok": not bad and plain == c["plain_bytes"],
                           "k1_ms": k1, "k4_ms": k4, "k3_ms": k3, "k1_GBps_out": plain / (k1 / 1e3) / 1e9 if k1 else 0,
                           "k1_alg_GBps": (plain + n_src) / (k1 / 1e3) / 1e9 if k1 else 0}), flush=True)
