@@ -226,16 +226,33 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 	b->k2_idx.clear();
 	b->k2_spans.clear();
 	b->k2_checksums = false;
-	// Big independent blocks (block maximum >= 1 MiB and >= 64 KiB of compressed bytes: ~10^5 sequences in series) are
-	// placed as chains of one block: K1 gives such a block one warp, which walks it at ~100 MB/s whatever the kernel
-	// generation, the chain kernel K7 gives it a CTA that parses and copies it without a serial walk (kernels_k7.cuh;
-	// 2.2x per stream measured on text).  Highly compressible big blocks (zero pages, RLE: a few KiB of compressed
-	// bytes, some giant matches) stay in K1, whose warp-wide copies are what they need.  LZ4B200_SOLO=0 turns the
-	// placement off (A/B switch).
-	static const bool solo_on = [] {
+	// Big independent blocks (>= 64 KiB of compressed bytes: >= 10^4 sequences in series) are placed as chains of one
+	// block while the batch holds few of them: K1 gives such a block one warp, which walks it at ~100 MB/s whatever
+	// the kernel generation; the chain kernel K7 gives it a CTA that parses and copies it without a serial walk
+	// (kernels_k7.cuh: 250 - 400 MB/s per stream) but spends 2.3x the instructions, so its whole-chip rate stops at
+	// 40 - 60 GB/s where K1 v4 with thousands of streams reaches 200 - 300.  Measured: 341 text blocks of 4 MiB 24.5 ms
+	// as chains against 41.8 ms in K1; ~550 blocks of 250 - 450 KiB 5.8 ms against ~4 ms.  Chains up to 400 big blocks
+	// per batch, K1 beyond.  Highly compressible big blocks (zero pages, RLE: a few KiB of
+	// compressed bytes, some giant matches) stay in K1 either way, whose warp-wide copies are what they need.
+	// LZ4B200_SOLO=0 turns the placement off, LZ4B200_SOLO_MAX=n moves the limit (A/B switches).
+	static const int solo_max = [] {
 		const char *e = getenv("LZ4B200_SOLO");
-		return !(e && e[0] == '0');
+		if (e && e[0] == '0') return 0;
+		const char *m = getenv("LZ4B200_SOLO_MAX");
+		return m ? atoi(m) : 400;
 	}();
+	bool solo_on = false;
+	if (solo_max > 0) {
+		size_t big = 0;
+		for (const FramePlan &fp : b->frames) {
+			if (!fp.independent && fp.n_blocks > 1) continue;
+			for (uint32_t i = 0; i < fp.n_blocks; i++) {
+				const lz4b200_blk_desc &d = b->descs[fp.first_block + i];
+				if (!(d.flags & LZ4B200_BLK_STORED) && d.src_len >= 65536) big++;
+			}
+		}
+		solo_on = big > 0 && big <= size_t(solo_max);
+	}
 	uint64_t cursor = 0;
 	for (ItemPlan &it : b->items) {
 		it.slow = false;
@@ -255,7 +272,7 @@ void place(lz4ada_batch *b, const std::vector<uint32_t> *sized_len)
 			fp.dst_off = pos;
 			fp.chained = !fp.independent && fp.n_blocks > 1;
 			// a big block is ~10^5 sequences in series: give it the chain kernel (one CTA)
-			fp.solo = solo_on && !fp.chained && fp.block_max >= (1u << 20);
+			fp.solo = solo_on && !fp.chained;
 			fp.hash_slot = 0xffffffffu;
 			// blocks sit one block-maximum apart (the frame format has no per-block decompressed size) -- unless K5
 			// has sized every block in front of this one (exact-sizing mode): then they sit back to back

@@ -73,7 +73,7 @@ struct Shared {
 	uint32_t bc[8];
 	__align__(16) uint16_t ptr[NWIN];
 	__align__(16) uint8_t win[NWIN];
-	__align__(16) uint8_t in[IN_BYTES + 16];   // (+ 16: the literal copy reads up to three bytes beyond a run)
+	__align__(16) uint8_t in[IN_BYTES + 16];   // (+ 16: the literal copy reads up to seven bytes beyond a run)
 };
 
 // (statistics, read by lz4b200_decode_linked under LZ4B200_K7_DEBUG: blocks finished, blocks given up, last reason, its block)
@@ -497,6 +497,8 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 								lp = tk.lp + bias;
 								if (lit_left == 0u && m_left == 0u) continue;
 							}
+							// up to four bytes of the run in progress (eight per turn, literals and match bytes under one
+							// roof, measured slower: 3.2 against 1.7 G cycles for the initialisation of 512 MiB)
 							if (lit_left) {
 								const uint32_t k = lit_left < 4u ? lit_left : 4u;
 								uint32_t v[4];

@@ -148,9 +148,12 @@ int lz4b200_sm_count(const lz4b200_ctx *ctx);
 uint64_t lz4b200_launch_count(const lz4b200_ctx *ctx);
 
 /* K1 tuning: which generation of the independent-block kernel lz4b200_decode_blocks launches.
- *    0        choose from the block count (default): v5 when the batch fills the chip (about 47 000
- *             blocks on a 148-SM part), v4 otherwise
- *   50        v5: one lane per block, 32 blocks in lock-step per warp, per-lane shared-memory rings
+ *    0        choose from the block count (default): v6 from 20 000 blocks on (a launch of v6 lasts as long as one
+ *             lane's block whatever the count, v4 costs ~0.37 us per 64 KiB text block), v4 below; the batch
+ *             scheduler, which has the block table, counts only the blocks that take long
+ *   60 / 61   v6: one lane per block, one piece of a sequence (<= 8 literal + <= 16 match bytes) per trip, the parse
+ *             K pieces ahead of the copy; 60 = 256-byte out ring per lane, 14 warps per SM; 61 = 512-byte ring, 8 warps
+ *   50        v5: one lane per block, a whole sequence per trip (round 1's kernel, kept for A/B)
  *   40        v4: one warp per block, warp-parallel parse, 4 KiB shared-memory output ring per warp;
  *             41 / 42 / 44 / 48 fix the number of blocks a warp hashes together and decodes in turn
  *   64        v3: one CTA per block, whole output window in shared memory (kept for A/B: slow)
@@ -220,10 +223,16 @@ int lz4b200_copy_stored(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, uint
 		uint32_t max_len, const lz4b200_blk_desc *desc, lz4b200_blk_status *status,
 		const lz4b200_hash_span *spans, uint32_t *scratch);
 
-/* K4: chains -- blocks in order by one warp, chains in parallel; the running output
+/* Chains -- the blocks of a chain in order, chains in parallel; the running output
  * position of the chain places every block, so matches may reach back across block
- * boundaries of the same frame (linked frames; also the exact-placement retry path).
- * Replaces the ring/history handling of lib/lz4ada.adb:678-680, 845-904. */
+ * boundaries of the same frame (linked frames; big independent blocks as chains of one;
+ * also the exact-placement retry path).  Replaces the ring/history handling of
+ * lib/lz4ada.adb:678-680, 845-904.  Kernel: K7 (one CTA per chain: speculative parallel
+ * parse + pointer jumping in a shared-memory window, kernels_k7.cuh), with the block
+ * checksums of all chained blocks hashed by a launch of their own in front of it.
+ * LZ4B200_CHAIN_KERNEL=pipe | k6 | warp in the environment selects the earlier generations
+ * (K4 pipeline, K6 rounds, one warp per chain) for A/B; LZ4B200_K7_DEBUG=1 prints K7's
+ * phase statistics after every launch. */
 int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst,
 		uint32_t n_chains, const lz4b200_chain *chains,
 		const lz4b200_blk_desc *desc, lz4b200_blk_status *status);

@@ -172,10 +172,9 @@ def test_block_table_builder(stem):
         assert bool(d.flags & 1) == stored
         assert bool(d.flags & 2) == bool(flg & 0x10)
         linked = not (flg & 0x20) and len(exp) > 1
-        # big compressed blocks of independent frames (block maximum >= 1 MiB, >= 64 KiB compressed) are placed as
-        # chains of one block (LZ4B200_BLK_SOLO) for the chain kernel; LZ4B200_SOLO=0 in the environment turns that off
-        solo = (os.environ.get("LZ4B200_SOLO", "") != "0" and not linked and ((data[5] >> 4) & 7) >= 6 and not stored
-                and n >= 65536)
+        # big compressed blocks of independent frames (>= 64 KiB compressed) are placed as chains of one block
+        # (LZ4B200_BLK_SOLO) for the chain kernel while a batch holds few of them; LZ4B200_SOLO=0 turns that off
+        solo = os.environ.get("LZ4B200_SOLO", "") != "0" and not linked and not stored and n >= 65536
         assert bool(d.flags & 32) == solo             # LZ4B200_BLK_SOLO
         assert bool(d.flags & 8) == (linked or solo)  # LZ4B200_BLK_CHAINED
         assert bool(d.flags & 16) == (i == 0 or solo) # LZ4B200_BLK_FIRST_OF_FRAME
