@@ -338,7 +338,9 @@ def roofline_of(r, peak, peak_src):
         name = "xxh32_frames_kernel (K3)"
     else:
         ach = cd / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else 0.0
-        name = (r["k1_name"] + " (K1)") if km["k1_decode_blocks"] >= km["k4_decode_linked"] else "decode_chain_pipe_kernel (K4)"
+        chain = {"pipe": "decode_chain_pipe_kernel (K4)", "k6": "decode_chain_k6_kernel (K6)", "warp": "decode_linked_kernel"}.get(
+            os.environ.get("LZ4B200_CHAIN_KERNEL", ""), "decode_chain_k7_kernel (K7)")
+        name = (r["k1_name"] + " (K1)") if km["k1_decode_blocks"] >= km["k4_decode_linked"] else chain
     return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": int(parts[top] if top == "k3_xxh32_frames" else cd),
             "whole_step_frac": (cd + tr["checksum_reread"]) / (r["ms_per_step"] / 1e3) / 1e9 / peak}

@@ -584,17 +584,8 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 						finish_window();
 						if (warp == 0) {
 							uint32_t lp = 0, lit = 0, ml = 0, nxt = 0, off = 0;
-							bool fine = true;
-							if (lane == 0) {
-								fine = parse_token(s, n, ip, lp, lit, ml, nxt);
-								if (fine && ml) off = ld_u8<true>(s + lp + lit) | (ld_u8<true>(s + lp + lit + 1) << 8);
-							}
-							fine = __shfl_sync(FULL_MASK, fine ? 1 : 0, 0) != 0;
-							lp = __shfl_sync(FULL_MASK, lp, 0);
-							lit = __shfl_sync(FULL_MASK, lit, 0);
-							ml = __shfl_sync(FULL_MASK, ml, 0);
-							nxt = __shfl_sync(FULL_MASK, nxt, 0);
-							off = __shfl_sync(FULL_MASK, off, 0);
+							bool fine = parse_token_wide(s, n, ip, lp, lit, ml, nxt, lane);
+							if (fine && ml) off = ld_u8<true>(s + lp + lit) | (ld_u8<true>(s + lp + lit + 1) << 8);
 							const uint32_t left = cap - (fpos - f0);
 							if (fine && (lit > left || ml > left - lit || (ml && (off == 0 || off > fpos + lit)))) fine = false;
 							if (fine) {

@@ -353,6 +353,35 @@ __device__ __forceinline__ bool parse_token(const uint8_t *__restrict__ s, uint3
 	return false;
 }
 
+// One token with lengths of any size, by the whole warp: the extension bytes are scanned 32 at a time
+// (read_length_ext; a 4 MiB run has 16 448 of them).  Same results as parse_token, without its 16-bit limit on the
+// fields; false for truncation and for lengths beyond 2^31.  Warp-uniform.
+__device__ __forceinline__ bool parse_token_wide(const uint8_t *__restrict__ s, uint32_t n, uint32_t ip, uint32_t &p,
+						 uint32_t &lit, uint32_t &ml, uint32_t &nxt, int lane)
+{
+	const uint32_t t = ld_u8<true>(s + ip);
+	lit = t >> 4;
+	ml = t & 15;
+	p = ip + 1;
+	if (lit == 15) {
+		if (!read_length_ext(s, p, n, lit, lane) || lit > 0x7fffffffu) return false;
+	}
+	if (lit > n - p) return false;
+	const uint32_t q = p + lit;
+	if (q == n) {
+		if (ml) return false;
+		nxt = n;
+		return true;
+	}
+	if (q + 2 > n) return false;
+	nxt = q + 2;
+	if (ml == 15) {
+		if (!read_length_ext(s, nxt, n, ml, lane) || ml > 0x7ffffff0u) return false;
+	}
+	ml += 4;
+	return true;
+}
+
 // One block of a chain by one warp through the batch machinery (lane 0 walks the token chain).
 // Positions are relative to `frame_out` (the start of the frame's flat output), so a match may
 // reach back across block boundaries; pos advances by what the block produced.  Returns false when

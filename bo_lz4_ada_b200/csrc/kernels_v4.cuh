@@ -60,9 +60,10 @@ constexpr uint32_t STOP = 0xffffffffu;
 // of this token (Decompress_Sequence, lib/lz4ada.adb:737-777; lengths: Process_Variable_Length :724-735).
 __device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint32_t wlen, uint32_t last, uint32_t &st)
 {
-	// A length with more than GIANT_EXT extension bytes (a run of 256 KiB and more: zero pages, RLE) ends the fast
-	// path for the block (W_BAD): the exact routine scans such lengths 32 bytes at a time and replicates the
-	// pattern with vector stores, while the speculative chains here would crawl through the 0xff bytes one by one.
+	// A length with more than GIANT_EXT extension bytes (a run of 256 KiB and more: zero pages, RLE) ends the window
+	// in front of its token (W_CUT): decode_block takes such a sequence on its own -- the whole warp scans the length
+	// 32 bytes at a time and copies in global memory -- while the speculative chains here would crawl through the
+	// 0xff bytes one by one.
 	constexpr uint32_t GIANT_EXT = 1024;
 	const uint32_t tk = cw[p];
 	uint32_t lit = tk >> 4, q = p + 1;
@@ -72,7 +73,7 @@ __device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint3
 		const uint32_t q0 = q;
 		do {
 			if (q >= wlen) { st = stop_st; return STOP; }
-			if (q - q0 > GIANT_EXT) { st = W_BAD; return STOP; }
+			if (q - q0 > GIANT_EXT) { st = W_CUT; return STOP; }
 			b = cw[q++];
 			lit += b;
 		} while (b == 255);
@@ -91,7 +92,7 @@ __device__ __noinline__ uint32_t token_slow(const uint8_t *cw, uint32_t p, uint3
 		const uint32_t n0 = nx;
 		do {
 			if (nx >= wlen) { st = stop_st; return STOP; }
-			if (nx - n0 > GIANT_EXT) { st = W_BAD; return STOP; }
+			if (nx - n0 > GIANT_EXT) { st = W_CUT; return STOP; }
 			b = cw[nx++];
 		} while (b == 255);
 	}
@@ -620,7 +621,19 @@ __device__ __forceinline__ bool decode_block(const uint8_t *__restrict__ s, uint
 		if (nuse == 0) return false;
 		const uint32_t T = __shfl_sync(FULL_MASK, ic, nuse - 1);
 		const uint32_t wend = __shfl_sync(FULL_MASK, r.x, nuse - 1);
-		if (wend == 0 || T == 0) return false;
+		if (wend == 0 || T == 0) {
+			// the window's first token does not complete inside it (a literal run longer than the window, a length
+			// field of hundreds of bytes): that one sequence straight in global memory, then on with the next window --
+			// not the whole block to the exact routine, which walks a 450 KiB block for 18 ms
+			uint32_t lp = 0, lit = 0, ml = 0, nxt = 0, off = 0;
+			const bool fine = parse_token_wide(s, n, ip, lp, lit, ml, nxt, lane);
+			if (fine && ml) off = ld_u8<true>(s + lp + lit) | (ld_u8<true>(s + lp + lit + 1) << 8);
+			const uint32_t left = cap - st.pos;
+			if (!fine || nxt <= ip || lit > left || ml > left - lit || (ml && (off == 0 || off > st.pos + lit))) return false;
+			slow_batch(wm.ring, phase, og, s, st, 1, lit, ml, off, lp, lit + ml, lane);
+			ip = nxt;
+			continue;
+		}
 		// ---------------- emit the token table ----------------
 		walk_segment<true>(cw, g, seg_hi, wlen, last, use && r.c != 0, ic - r.c, wm.tokpos);
 		__syncwarp();
