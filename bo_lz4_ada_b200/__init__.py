@@ -140,6 +140,7 @@ _SIGNATURES = {
     "lz4b200_get_tuning": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_k1_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
     "lz4b200_k1_fallbacks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
+    "lz4b200_chain_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     "lz4b200_use_lane": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "lz4b200_sync_all": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4b200_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -318,6 +319,12 @@ class DeviceContext:
         """(blocks the last v6 launch handed to the exact routine, of those by the safety net)"""
         a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
         lib().lz4b200_k1_fallbacks(self.handle, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def chain_stats(self):
+        """(blocks the chain kernel K7 finished, blocks it gave to the exact routine) since the last call"""
+        a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._ck(lib().lz4b200_chain_stats(self.handle, ctypes.byref(a), ctypes.byref(b)), "lz4b200_chain_stats")
         return a.value, b.value
 
     def alloc(self, nbytes):

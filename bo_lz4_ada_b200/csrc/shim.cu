@@ -1255,6 +1255,20 @@ int lz4b200_k1_fallbacks(lz4b200_ctx *ctx, uint32_t *to_exact, uint32_t *by_safe
 	return LZ4B200_OK;
 }
 
+int lz4b200_chain_stats(lz4b200_ctx *ctx, uint32_t *finished, uint32_t *given_up)
+{
+	if (!ctx) return LZ4B200_ERR_ARG;
+	uint32_t h[8] = {};
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyFromSymbol(h, k7::g_stats, sizeof h));
+	if (finished) *finished = h[0];
+	if (given_up) *given_up = h[1];
+	memset(h, 0, sizeof h);
+	CK(cudaMemcpyToSymbol(k7::g_stats, h, sizeof h));
+	return LZ4B200_OK;
+}
+
 // the auto rule of lz4b200_decode_blocks, in one place
 static int k1_generation(const lz4b200_ctx *ctx, uint32_t n_blocks)
 {

@@ -237,6 +237,10 @@ int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst,
 		uint32_t n_chains, const lz4b200_chain *chains,
 		const lz4b200_blk_desc *desc, lz4b200_blk_status *status);
 
+/* Statistics of the chain kernel K7 since the last call (per device, all contexts): blocks its fast path finished, and
+ * blocks it gave up on (that block and the rest of its chain went to the exact routine).  Synchronises the lane; resets. */
+int lz4b200_chain_stats(lz4b200_ctx *ctx, uint32_t *finished, uint32_t *given_up);
+
 /* K3: XXH32 (seed 0) of `n` byte ranges, one serial chain per range, ranges in
  * parallel.  Takes over Update_Checksum / XXHash32.Update / Final for the
  * content checksum (lib/lz4ada.adb:709-714, 942-1017). */

@@ -1118,6 +1118,99 @@ def test_pipelined_chains_repeatable(ctx):
             assert out == plain, rep
 
 
+def _run_chains_direct(ctx, chains_of_blocks, cap_per_block, checksums=False, corrupt=()):
+    """lz4b200_decode_linked on hand-made chains (lists of raw blocks): the blocks of a chain are one frame, output back
+    to back.  Returns per chain [(code, out_len, computed, declared)] and the chain's output bytes."""
+    src = bytearray(b"\0" * 16)
+    descs, chains = [], []
+    dst_pos = 0
+    for blocks in chains_of_blocks:
+        first = len(descs)
+        for i, blk in enumerate(blocks):
+            d = lz.BlkDesc()
+            d.src_off, d.src_len = len(src), len(blk)
+            d.dst_off, d.dst_cap = dst_pos, cap_per_block
+            d.flags = 8 | (16 if i == 0 else 0) | (2 if checksums else 0)   # CHAINED, FIRST_OF_FRAME, HAS_CHECKSUM
+            d.hist_avail = 0
+            src += blk
+            if checksums:
+                h = corpus.xxh32(blk) ^ (1 if len(descs) in corrupt else 0)
+                src += struct.pack("<I", h)
+            src += b"\0" * (len(descs) % 5)   # every source alignment
+            descs.append(d)
+        c = lz.Chain()
+        c.first_block, c.n_blocks = first, len(blocks)
+        c.dst_off, c.dst_cap = dst_pos + 3 * len(chains), cap_per_block * len(blocks)   # every destination alignment
+        chains.append(c)
+        dst_pos += cap_per_block * len(blocks) + 256
+    src += b"\0" * 64
+    da = (lz.BlkDesc * len(descs))(*descs)
+    ca = (lz.Chain * len(chains))(*chains)
+    d_src, d_dst = ctx.alloc(len(src)), ctx.alloc(dst_pos + 256)
+    d_desc, d_st, d_ch = ctx.alloc(ctypes_sizeof(da)), ctx.alloc(24 * len(descs)), ctx.alloc(ctypes_sizeof(ca))
+    ctx.h2d(d_src, bytes(src))
+    ctx.h2d(d_desc, bytes(da))
+    ctx.h2d(d_ch, bytes(ca))
+    assert lz.lib().lz4b200_memset(ctx.handle, d_st, 0xff, 24 * len(descs)) == 0
+    assert lz.lib().lz4b200_decode_linked(ctx.handle, d_src, d_dst, len(chains), d_ch, d_desc, d_st) == 0
+    ctx.sync()
+    st = ctx.d2h(d_st, 24 * len(descs))
+    out = ctx.d2h(d_dst, dst_pos + 256)
+    res = []
+    for c in chains:
+        rows = [struct.unpack_from("<IIIiII", st, 24 * (c.first_block + i)) for i in range(c.n_blocks)]
+        n = sum(r[1] for r in rows if r[0] == 0)
+        res.append((rows, out[c.dst_off:c.dst_off + n]))
+    for p_ in (d_src, d_dst, d_desc, d_st, d_ch):
+        ctx.free(p_)
+    return res
+
+
+def test_chain_kernel_shapes_direct(ctx):
+    """The chain kernel (K7 by default) straight through lz4b200_decode_linked: the hand-made shapes of the K1 tests as
+    chains of one block (dense 3-byte sequences, literal runs of 30 000 / 40 000 bytes -- longer than the staged bytes --
+    giant matches at every small offset, lengths around every nibble / extension threshold), multi-block chains whose
+    matches reach back across block boundaries, every source and destination alignment, block checksums hashed by the
+    kernel in front (one of them wrong: that block and the rest of its chain must not be reported as decoded)."""
+    rng = np.random.default_rng(123)
+    shapes = _v3_shape_blocks()
+    ctx.chain_stats()
+    res = _run_chains_direct(ctx, [[b] for b in shapes], 65536 + 64)
+    for blk, (rows, out) in zip(shapes, res):
+        exp = _py_decode(blk)
+        assert rows[0][0] == 0 and rows[0][1] == len(exp), (len(blk), rows[0])
+        assert out == exp, len(blk)
+    if not os.environ.get("LZ4B200_CHAIN_KERNEL"):
+        assert ctx.chain_stats() == (len(shapes), 0)   # all of them on K7's fast path, none through the exact routine
+    # linked chains: one long text compressed block by block against the previous 64 KiB
+    text = corpus.text_like(900000, seed=11) + bytes(70000) + corpus.random_bytes(5000, seed=2) + corpus.text_like(100000, seed=12)
+    chains, plains = [], []
+    for bs in (65536, 262144, 20000):
+        blocks, pos = [], 0
+        while pos < len(text):
+            piece = text[pos:pos + bs]
+            blocks.append(corpus.compress_block(piece, prefix=text[max(0, pos - 65536):pos]))
+            pos += bs
+        if all(b is not None for b in blocks):
+            chains.append(blocks)
+            plains.append(text)
+    assert chains
+    for checks in (False, True):
+        bad = (3,) if checks else ()
+        res = _run_chains_direct(ctx, chains, 262144 + 64, checksums=checks, corrupt=bad)
+        for k, ((rows, out), plain) in enumerate(zip(res, plains)):
+            if checks and k == 0:
+                # block 3 of the first chain carries a wrong checksum (lib/lz4ada.adb:698-707): reported there, nothing after it
+                assert [r[0] for r in rows[:3]] == [0, 0, 0] and rows[3][0] == 1 and rows[3][4] != rows[3][5], rows[:5]
+                assert all(r[0] != 0 for r in rows[3:])
+                assert out == plain[:len(out)] and len(out) == 3 * 65536
+            else:
+                assert all(r[0] == 0 for r in rows), (k, [r[0] for r in rows])
+                assert out == plain, k
+        if not os.environ.get("LZ4B200_CHAIN_KERNEL"):
+            assert ctx.chain_stats()[1] == (1 if checks else 0)
+
+
 @pytest.mark.parametrize("chain,solo", [("k7", "1"), ("k7", "0"), ("k6", "1"), ("k6", "0"), ("warp", "1"), ("pipe", "1")])
 def test_chain_kernel_variants(chain, solo):
     """The chain kernels are chosen once per process from the environment: K6 (pointer-doubling parser + round-based
