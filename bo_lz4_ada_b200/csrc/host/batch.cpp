@@ -1213,7 +1213,10 @@ int lz4ada_batch_decompress(lz4b200_ctx *ctx, const uint8_t *src_host, uint64_t 
 	if (b->placed && b->descs.size()) {
 		// fast shape: placement is known without touching the device -> pipeline H2D / kernels / D2H
 		rc = lz4ada_batch_upload(b, nullptr, nullptr);   // tables only
-		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(8, plain_guess >> 29)));   // ~512 MiB of output each
+		// ~512 MiB of output per chunk, at most 8 (LZ4ADA_E2E_CHUNKS / LZ4ADA_E2E_CHUNK_SHIFT: experiments)
+		static const uint32_t max_chunks = [] { const char *e = getenv("LZ4ADA_E2E_CHUNKS"); return e ? uint32_t(atoi(e)) : 8u; }();
+		static const uint32_t chunk_shift = [] { const char *e = getenv("LZ4ADA_E2E_CHUNK_SHIFT"); return e ? uint32_t(atoi(e)) : 29u; }();
+		const uint32_t chunks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(max_chunks, plain_guess >> chunk_shift)));
 		if (rc == LZ4ADA_OK) rc = lz4ada_batch_run_pipelined(b, src_host, dst_host, d_src, d_dst, chunks);
 	} else {
 		rc = lz4ada_batch_upload(b, src_host, d_src);

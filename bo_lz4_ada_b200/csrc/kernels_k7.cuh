@@ -57,8 +57,14 @@ __device__ __forceinline__ uint32_t first_bit(mask_t m) { return static_cast<uin
 constexpr uint32_t STEP = T * S;               // 8 KiB
 constexpr uint32_t SLACK = 1024;               // staged beyond the step: tokens of the last segments complete in here
 constexpr uint32_t IN_BYTES = STEP + SLACK + 32;
-constexpr uint32_t NWIN = 16384;               // output window (pointers are 16 bits)
-constexpr uint32_t LONG = 64;                  // literal runs / matches from here on are initialised by a warp
+#ifndef LZ4B200_K7_NWIN
+#define LZ4B200_K7_NWIN 16384
+#endif
+constexpr uint32_t NWIN = LZ4B200_K7_NWIN;     // output window (pointers are 16 bits)
+#ifndef LZ4B200_K7_LONG
+#define LZ4B200_K7_LONG 64
+#endif
+constexpr uint32_t LONG = LZ4B200_K7_LONG;                  // literal runs / matches from here on are initialised by a warp
 // where a walk left its segment: the block position of the next token, or
 constexpr uint32_t EX_END = 0xffffffffu;       // the block's last sequence has been consumed
 constexpr uint32_t EX_ERR = 0xfffffffeu;       // a token that cannot be (the exact routine says why)
@@ -71,6 +77,8 @@ struct Shared {
 	uint16_t jmp[2][T];
 	uint32_t wsum[WARPS], longs[WARPS];
 	uint32_t bc[8];
+	uint8_t nxt[T * (S + 4)];   // next-token table of the step: segment t, byte o at t * (S + 4) + o (a padded row per segment:
+	                            // the lanes of a warp read their segments in different banks)
 	__align__(16) uint16_t ptr[NWIN];
 	__align__(16) uint8_t win[NWIN];
 	__align__(16) uint8_t in[IN_BYTES + 16];   // (+ 16: the literal copy reads up to seven bytes beyond a run)
@@ -336,9 +344,31 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 				const uint32_t hi = n < base16 + IN_BYTES - mis ? n : base16 + IN_BYTES - mis;
 				const uint32_t x_t = ip + tid * S, seg_end = x_t + S;
 
-				// ---- parse: every thread walks its segment from its first byte; then the true chain is threaded through ----
+				// ---- parse: "where is the next token if one starts here" for every byte of the step, all threads side by
+				// side (consecutive lanes take consecutive bytes); 255 = look again when a walk gets there ----
+				// (only the plain token -- both nibbles below 15, the sequence inside the staged bytes and not the block's
+				// last -- is worked out here: token + literals + offset = 3 + the literal nibble.  Everything else is 255
+				// and parsed by the walk that gets there: filling those in here as well cost 4x the cycles, every warp
+				// taking the slow path for the one lane in eight that needs it)
+				{
+					const uint32_t lim = n < hi ? n : hi;
+					for (uint32_t k = tid; k < STEP; k += T) {
+						const uint32_t x = ip + k;
+						uint32_t d = 255u;
+						if (x < lim) {
+							const uint32_t tk = sh.in[x + bias];
+							const uint32_t step = 3u + (tk >> 4);
+							if ((tk >> 4) != 15u && (tk & 15u) != 15u && x + step <= lim) d = step;
+						}
+						sh.nxt[(k / S) * (S + 4u) + (k % S)] = static_cast<uint8_t>(d);
+					}
+				}
+				__syncthreads();
+				const long long tq1 = clock64();
+				// every thread walks its segment from its first byte; then the true chain is threaded through
 				mask_t my_mask = 0;
 				uint32_t my_exit = EX_ERR;
+				const uint8_t *my_row = sh.nxt + tid * (S + 4u);
 				auto walk = [&](uint32_t x0, bool merge) {
 					mask_t m = 0;
 					uint32_t x = x0, ex;
@@ -350,19 +380,50 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 							ex = my_exit;
 							break;
 						}
-						Tok tk;
-						const uint32_t c = parse_tok(sh.in, bias, x, n, hi, tk);
-						if (c == TK_UNSTAGED) { ex = EX_STOP | x; break; }
-						if (c == TK_ERR) { ex = EX_ERR; break; }
+						uint32_t d = my_row[x - x_t];
+						if (d == 255u) {
+							Tok tk;
+							const uint32_t c = parse_tok(sh.in, bias, x, n, hi, tk);
+							if (c == TK_UNSTAGED) { ex = EX_STOP | x; break; }
+							if (c == TK_ERR) { ex = EX_ERR; break; }
+							d = tk.nxt - x;
+						}
 						m |= mask_t(1) << (x - x_t);
-						x = tk.nxt;
+						x += d;
 					}
 					my_mask = m;
 					my_exit = ex;
 				};
 				const bool inside = x_t < n;
+				// the guess: not "a token starts at my first byte" (true one time in four) but where a walk that started
+				// two segments earlier enters my segment -- by then it has met the real chain 9 times out of 10, so most
+				// segments start out right and the iterations below are few.  (The table makes the run-up cheap.)
 				uint32_t ent = x_t;
-				if (inside) walk(x_t, false);
+				if (inside && tid > 0) {
+					uint32_t p = tid >= 2 ? x_t - 2u * S : ip;
+					while (p < x_t) {
+						const uint32_t k = p - ip;
+						uint32_t d = sh.nxt[(k / S) * (S + 4u) + (k % S)];
+						if (d == 255u) {
+							Tok tk;
+							if (parse_tok(sh.in, bias, p, n, hi, tk) != TK_OK) { p = x_t; break; }   // (no guess: my first byte then)
+							d = tk.nxt - p;
+						}
+						p += d;
+					}
+					ent = p;
+				}
+				if (inside) {
+					if (ent < seg_end) {
+						walk(ent, false);
+					} else {
+						my_mask = 0;      // the run-up jumps over my segment: nothing to say until a neighbour's exit lands here
+						my_exit = ent;
+						ent = 0xffffffffu;
+					}
+				}
+				__syncthreads();
+				const long long tq2 = clock64();
 				// (1) neighbours: a segment's entry point is where the one in front of it leaves off.  No segment is ever
 				// dropped here -- a guessed path that jumps far (a literal byte read as a token) must not silence the segments
 				// it jumps over, they are most likely right -- so this settles in as many iterations as the longest run of
@@ -386,6 +447,7 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 				// "the segment my exit lands in"), and does each of them start where that path enters it?  Those that do not
 				// (behind a long literal run their neighbour is a guess inside the literals) walk again; the rest keeps to
 				// rule (1).  At the fixed point the segments on the path from thread 0 hold the block's true tokens.
+				const long long tq3 = clock64();
 				bool active = false;
 				uint32_t link = T;
 				for (;;) {
@@ -461,6 +523,10 @@ __device__ __forceinline__ uint32_t run_chain(Shared &sh, const lz4b200_chain &c
 				if (tid == 0) {
 					atomicAdd(&g_prof[0], 1ull);
 					atomicAdd(&g_prof[4], static_cast<unsigned long long>(tp1 - tp0));
+					atomicAdd(&g_prof[11], static_cast<unsigned long long>(tq1 - tp1));
+					atomicAdd(&g_prof[12], static_cast<unsigned long long>(tq2 - tq1));
+					atomicAdd(&g_prof[13], static_cast<unsigned long long>(tq3 - tq2));
+					atomicAdd(&g_prof[14], static_cast<unsigned long long>(tp2 - tq3));
 					atomicAdd(&g_prof[5], static_cast<unsigned long long>(tp2 - tp1));
 					atomicAdd(&g_prof[6], static_cast<unsigned long long>(tp3 - tp2));
 				}

@@ -1588,8 +1588,8 @@ int lz4b200_decode_linked(lz4b200_ctx *ctx, const uint8_t *src, uint8_t *dst, ui
 			CK(cudaMemcpyToSymbol(k7::g_stats, h, sizeof h));
 			unsigned long long q[16] = {};
 			CK(cudaMemcpyFromSymbol(q, k7::g_prof, sizeof q));
-			fprintf(stderr, "[lz4b200 k7] steps %llu, parse iterations %llu, resolve calls %llu rounds %llu; kilocycles (thread 0, summed over CTAs): stage %llu parse %llu place %llu windows %llu (init %llu resolve %llu flush %llu)\n",
-				q[0], q[1], q[2], q[3], q[4] >> 10, q[5] >> 10, q[6] >> 10, q[7] >> 10, q[10] >> 10, q[8] >> 10, q[9] >> 10);
+			fprintf(stderr, "[lz4b200 k7] steps %llu, parse iterations %llu, resolve calls %llu rounds %llu; kilocycles (thread 0, summed over CTAs): stage %llu parse %llu place %llu windows %llu (init %llu resolve %llu flush %llu); parse = table %llu + first walk %llu + neighbours %llu + path %llu\n",
+				q[0], q[1], q[2], q[3], q[4] >> 10, q[5] >> 10, q[6] >> 10, q[7] >> 10, q[10] >> 10, q[8] >> 10, q[9] >> 10, q[11] >> 10, q[12] >> 10, q[13] >> 10, q[14] >> 10);
 			memset(q, 0, sizeof q);
 			CK(cudaMemcpyToSymbol(k7::g_prof, q, sizeof q));
 		}
