@@ -135,4 +135,11 @@ private package LZ4Ada.Device is
    function K1_Kernel_Name (Ctx : Context; N_Blocks : Unsigned_32) return Interfaces.C.Strings.chars_ptr
      with Import, Convention => C, External_Name => "lz4b200_k1_kernel_name";
 
+   --  statistics for a maintainer: blocks the lane-per-block K1 (v6) handed to the exact routine in its last launch,
+   --  blocks the chain kernel (K7) finished / gave up on since the last call
+   function K1_Fallbacks (Ctx : Context; To_Exact, By_Safety_Net : out Unsigned_32) return int
+     with Import, Convention => C, External_Name => "lz4b200_k1_fallbacks";
+   function Chain_Stats (Ctx : Context; Finished, Given_Up : out Unsigned_32) return int
+     with Import, Convention => C, External_Name => "lz4b200_chain_stats";
+
 end LZ4Ada.Device;

@@ -6,18 +6,19 @@
 // times the instructions of a sequence.  A stream is serial twice, and K7 breaks both chains with work instead of
 // waiting:
 //
-//   parse    the compressed bytes are staged in shared memory 8 KiB at a time (a step); every thread owns a 32-byte
-//            segment and parses from its first byte AS IF a token started there (a wrong guess soon falls in step
-//            with the real token chain: on text a guessed path meets the real one inside its own segment 56 times
-//            out of 100).  It keeps the positions it visited as a bit mask and where it left the segment.  The true
-//            chain is then threaded through the segments: first every segment takes the exit of the one in front
-//            of it as its entry point and walks again from there until it meets the path it knows (a few tokens)
-//            -- ~10 iterations, as long as the longest run of segments whose guess and truth do not meet; then the
-//            path from segment 0 is marked by pointer jumping over "the segment my exit lands in" and the segments
-//            on it are checked against the entry points that path really gives them (behind a long literal run the
-//            neighbour is a guess made inside the literals) -- one or two iterations more.  Decompress_Sequence's
-//            length arithmetic, lib/lz4ada.adb:737-777, is all a walk needs.  tests/test_k7_model_cpu.py is this
-//            scheme in Python, checked against the real token chain
+//   parse    the compressed bytes are staged in shared memory 8 KiB at a time (a step).  All threads side by side
+//            fill a next-token table for the plain tokens (both nibbles below 15: 3 + the literal nibble bytes on).
+//            Every thread then owns a 32-byte segment: it guesses its entry point by running up from two segments
+//            earlier (a guessed path soon falls in step with the real token chain: on text it meets it inside one
+//            segment 56 times out of 100), walks its segment, keeps the positions it visited as a bit mask and
+//            where it left the segment.  The true chain is then threaded through the segments: first every segment
+//            takes the exit of the one in front of it as its entry point and walks again from there until it meets
+//            the path it knows (a few tokens) -- as many iterations as the longest run of segments whose guess and
+//            truth do not meet; then the path from segment 0 is marked by pointer jumping over "the segment my exit
+//            lands in" and the segments on it are checked against the entry points that path really gives them
+//            (behind a long literal run the neighbour is a guess made inside the literals) -- one or two iterations
+//            more; 8 in all on text.  Decompress_Sequence's length arithmetic, lib/lz4ada.adb:737-777, is all a walk
+//            needs.  tests/test_k7_model_cpu.py is this scheme in Python, checked against the real token chain
 //   place    sequence lengths summed per segment, one scan over the CTA: every sequence knows its output position
 //   window   the output is built 16 KiB at a time in shared memory.  Every thread writes its own sequences: literal
 //            bytes are final at once (Write_Output, :790-824); a match byte whose source lies in front of the window
