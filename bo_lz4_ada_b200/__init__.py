@@ -161,6 +161,7 @@ _SIGNATURES = {
     "lz4b200_event_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "lz4b200_event_destroy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "lz4b200_event_sync": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "lz4b200_event_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.POINTER(ctypes.c_float)]),
     "lz4b200_decode_blocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
@@ -184,6 +185,8 @@ _SIGNATURES = {
                                              ctypes.POINTER(BlkStatus)]),
     "lz4b200_stream_digest": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32)]),
     "lz4b200_stream_adopt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]),
+    "lz4b200_stream_adopt_list": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32),
+                                                 ctypes.POINTER(ctypes.c_uint32), ctypes.c_int]),
     # LZ4Ada API
     "lz4ada_set_device_context": (ctypes.c_int, [ctypes.c_void_p]),
     "lz4ada_init": (ctypes.c_int, [c_int_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),

@@ -14,6 +14,8 @@
 // (history window + running content checksum).  Every call still reports exactly one block, the same
 // Num_Consumed / Output_First / Output_Last as the reference, and an erroneous block is never
 // cached: it goes through the one-block path when its turn comes, with the same exception.
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -54,11 +56,20 @@ public:
 	{
 		if (ctx_) {
 			if (d_src_) lz4b200_free(ctx_, d_src_);
-			if (d_stage_) lz4b200_free(ctx_, d_stage_);
+			for (int k = 0; k < 2; k++) {
+				if (d_stage_[k]) lz4b200_free(ctx_, d_stage_[k]);
+				if (hash_done_[k]) lz4b200_event_destroy(ctx_, hash_done_[k]);
+			}
+			if (h_copy_) lz4b200_free_host(ctx_, h_copy_);
 			if (d_desc_) lz4b200_free(ctx_, d_desc_);
 			if (d_stat_) lz4b200_free(ctx_, d_stat_);
-			if (h_stage_) lz4b200_free_host(ctx_, h_stage_);
+			for (int k = 0; k < 2; k++)
+				if (h_stage_[k]) lz4b200_free_host(ctx_, h_stage_[k]);
 		}
+		if (getenv("LZ4ADA_UPDATE_DEBUG") && dbg_n_served_)
+			fprintf(stderr, "[lz4ada update] %ld read-aheads %.1f ms (scan %.1f, reserve %.1f, enqueue %.1f, sync %.1f, keep %.1f), %ld blocks served %.1f ms; all of block() %.1f ms, content checksums %.1f ms\n",
+				dbg_n_ahead_, dbg_ahead_ * 1e3, dbg_stage_[0] * 1e3, dbg_stage_[1] * 1e3, dbg_stage_[2] * 1e3, dbg_stage_[3] * 1e3, dbg_stage_[4] * 1e3,
+				dbg_n_served_, dbg_serve_ * 1e3, dbg_stage_[5] * 1e3, dbg_digest_ * 1e3);
 		if (stream_) lz4b200_stream_destroy(stream_);
 		if (ctx_) lz4b200_destroy(ctx_);   // the engine's reference (default_context took it)
 	}
@@ -67,12 +78,23 @@ public:
 	{
 		output_pos_ = 0;
 		drop_ahead();
+		pend_off_.clear();   // (the old frame's checksum, if it had one, has been asked for by now: content_checksum flushes)
+		pend_len_.clear();
+		if (stream_ && !join_hash_lane()) return device_failure();
 		if (stream_ && lz4b200_stream_reset(stream_) != LZ4B200_OK) return device_failure();
 		return ok();
 	}
 
 	Raised block(Walker &w, const uint8_t *blk, int blk_len, uint8_t *buffer, int buffer_len, int &of,
 		     int &ol) override   // Decode_Full_Block_With_Trailer, :661-696
+	{
+		const double t_in = dbg_now();
+		const Raised r = block_inner(w, blk, blk_len, buffer, buffer_len, of, ol);
+		dbg_stage_[5] += dbg_now() - t_in;
+		return r;
+	}
+
+	Raised block_inner(Walker &w, const uint8_t *blk, int blk_len, uint8_t *buffer, int buffer_len, int &of, int &ol)
 	{
 		if (Raised r = ensure_stream()) return r;
 		const int raw_len = blk_len - w.m.block_checksum_length;
@@ -89,29 +111,49 @@ public:
 		bool served = false;
 		if (ahead_pos_ < ahead_.size()) {
 			const Ahead &e = ahead_[ahead_pos_];
-			if (e.blk_len == blk_len && e.flags == flags && memcmp(blk, ahead_copy_.data() + e.copy_off, size_t(blk_len)) == 0)
+			if (e.blk_len == blk_len && e.flags == flags && memcmp(blk, h_copy_ + e.copy_off, size_t(blk_len)) == 0)
 				served = true;
 			else
 				drop_ahead();   // the caller came back with something else
 		}
-		if (!served && ahead_pos_ >= ahead_.size() && w.lookahead && read_ahead(w, blk, blk_len, flags)) served = true;
+		if (!served && ahead_pos_ >= ahead_.size() && w.lookahead) {
+			const double t0 = dbg_now();
+			if (!flush_pending()) return device_failure();   // (the staging buffer is about to be overwritten)
+			if (read_ahead(w, blk, blk_len, flags)) served = true;
+			dbg_ahead_ += dbg_now() - t0;
+			dbg_n_ahead_++;
+		}
 		if (served) {
+			const double t0 = dbg_now();
+			dbg_n_served_++;
 			const Ahead &e = ahead_[ahead_pos_];
 			if (int64_t(e.st.out_len) <= cap) {
 				st = e.st;
-				if (st.out_len) memcpy(buffer + output_pos_, h_stage_ + e.out_off, st.out_len);
-				if (lz4b200_stream_adopt(stream_, d_stage_ + e.out_off, st.out_len, w.m.content_checksum_length != 0) != LZ4B200_OK)
-					return device_failure();
+				if (st.out_len) memcpy(buffer + output_pos_, h_stage_[cur_] + e.out_off, st.out_len);
+				// the stream adopts the block (history window + running content checksum) later, together with the
+				// other blocks served from this read-ahead: one hash launch and one window copy for all of them
+				pend_off_.push_back(e.out_off);
+				pend_len_.push_back(st.out_len);
+				pend_hash_ = w.m.content_checksum_length != 0;
+				pend_buf_ = cur_;
 				ahead_pos_++;
+				dbg_serve_ += dbg_now() - t0;
 			} else {
 				served = false;   // does not fit the caller's Buffer here: the one-block path reports it
 				drop_ahead();
 			}
 		}
+		const double t_single = dbg_now();
+		if (!served && (!flush_pending() || !join_hash_lane())) return device_failure();
+		if (!served) dbg_join_ += dbg_now() - t_single;
 		if (!served &&
 		    lz4b200_stream_block2(stream_, blk, uint32_t(raw_len), flags, w.m.content_checksum_length != 0,
 					  buffer + output_pos_, uint32_t(cap), uint32_t(w.m.frame_block_max), &st) != LZ4B200_OK)
 			return device_failure();
+		if (!served) {
+			dbg_single_ += dbg_now() - t_single;
+			dbg_n_single_++;
+		}
 		// Decrease_Data_Size_Remaining (:826-839) fires inside Write_Output, i.e. before any
 		// later check of the same block; the block checksum (:672-676) comes before everything.
 		if (w.m.has_content_size && st.code != LZ4B200_ST_BLOCK_CHECKSUM) {
@@ -129,8 +171,15 @@ public:
 	Raised content_checksum(Walker &, uint32_t declared) override   // :493-511
 	{
 		if (Raised r = ensure_stream()) return r;
+		const double t_in = dbg_now();
+		if (!flush_pending() || !join_hash_lane()) return device_failure();
 		uint32_t computed = 0;
 		if (lz4b200_stream_digest(stream_, &computed) != LZ4B200_OK) return device_failure();
+		dbg_digest_ += dbg_now() - t_in;
+		if (getenv("LZ4ADA_UPDATE_DEBUG"))
+			fprintf(stderr, "[lz4ada update, cumulative at frame end] read-aheads %ld: %.1f ms (pinned copy + buffers %.1f, enqueue %.1f, sync %.1f); served %ld: %.1f ms; one-block path %ld: %.1f ms (of which waiting for the hash lane %.1f); all of block() %.1f ms; content checksums %.1f ms\n",
+				dbg_n_ahead_, dbg_ahead_ * 1e3, dbg_stage_[1] * 1e3, dbg_stage_[2] * 1e3, dbg_stage_[3] * 1e3, dbg_n_served_, dbg_serve_ * 1e3,
+				dbg_n_single_, dbg_single_ * 1e3, dbg_join_ * 1e3, dbg_stage_[5] * 1e3, dbg_digest_ * 1e3);
 		if (computed != declared) return err_content_checksum(computed, declared);
 		return ok();
 	}
@@ -144,14 +193,14 @@ public:
 private:
 	// ---- read-ahead -----------------------------------------------------------------------
 	struct Ahead {
-		size_t copy_off;          // payload (+ trailer) of the block in ahead_copy_
+		size_t copy_off;          // payload (+ trailer) of the block in h_copy_
 		int blk_len;
 		uint32_t flags;
 		uint32_t out_off;         // its decoded bytes in the staging buffers
 		lz4b200_blk_status st;    // always LZ4B200_ST_OK
 	};
-	static constexpr int kAheadMaxBlocks = 64;
-	static constexpr uint64_t kAheadMaxBytes = 32ull << 20;   // decoded bytes per read-ahead
+	static constexpr int kAheadMaxBlocks = 255;               // (what lz4b200_stream_adopt_list takes at once)
+	static constexpr uint64_t kAheadMaxBytes = 64ull << 20;   // decoded bytes per read-ahead
 
 	void drop_ahead()
 	{
@@ -159,11 +208,52 @@ private:
 		ahead_pos_ = 0;
 	}
 
+	// (LZ4ADA_UPDATE_DEBUG=1: where the time of the read-ahead path goes, printed when the decompressor is freed)
+	static double dbg_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	double dbg_ahead_ = 0, dbg_serve_ = 0, dbg_digest_ = 0, dbg_stage_[6] = {0, 0, 0, 0, 0, 0};
+	long dbg_n_ahead_ = 0, dbg_n_served_ = 0, dbg_n_single_ = 0;
+	double dbg_single_ = 0, dbg_join_ = 0;
+	// Blocks served from the staging buffer that the stream has not adopted yet (offsets into d_stage_, in order).
+	std::vector<uint32_t> pend_off_, pend_len_;
+	bool pend_hash_ = false;
+	int pend_buf_ = 0;
+	bool hash_lane_busy_ = false;
+	void *hash_done_[2] = {nullptr, nullptr};   // events: the hash lane has passed the adoption that reads staging buffer k
+	bool hash_reads_[2] = {false, false};
+	// The adoption (one hash launch over all pending blocks + the window copy) runs on a lane of its own, so that the
+	// serial content checksum of one read-ahead (8 ms for 16 MiB) overlaps with the decode of the next; the two
+	// staging buffers alternate, and whoever needs the stream's state on the main lane joins the hash lane first.
+	bool flush_pending()
+	{
+		if (pend_off_.empty()) return true;
+		bool fine = lz4b200_use_lane(ctx_, 1) == LZ4B200_OK;
+		fine = fine && lz4b200_stream_adopt_list(stream_, d_stage_[pend_buf_], uint32_t(pend_off_.size()), pend_off_.data(), pend_len_.data(),
+							   pend_hash_ ? 1 : 0) == LZ4B200_OK;
+		if (fine && !hash_done_[pend_buf_]) fine = lz4b200_event_create(ctx_, &hash_done_[pend_buf_]) == LZ4B200_OK;
+		fine = fine && lz4b200_event_record(ctx_, hash_done_[pend_buf_]) == LZ4B200_OK;
+		lz4b200_use_lane(ctx_, 0);
+		hash_lane_busy_ = true;
+		hash_reads_[pend_buf_] = true;
+		pend_off_.clear();
+		pend_len_.clear();
+		return fine;
+	}
+	bool join_hash_lane()
+	{
+		if (!hash_lane_busy_) return true;
+		bool fine = lz4b200_use_lane(ctx_, 1) == LZ4B200_OK && lz4b200_sync(ctx_) == LZ4B200_OK;
+		lz4b200_use_lane(ctx_, 0);
+		hash_lane_busy_ = false;
+		hash_reads_[0] = hash_reads_[1] = false;
+		return fine;
+	}
+
 	// Decode `blk` and the complete independent blocks behind it in the caller's Input with one K1 launch.
 	// true = the cache now starts with `blk` (decoded fine); false = nothing cached, use the one-block path.
 	bool read_ahead(Walker &w, const uint8_t *blk, int blk_len, uint32_t flags)
 	{
 		drop_ahead();
+		const double ta = dbg_now();
 		if (w.m.format != Format::Modern || !w.m.block_independent || w.lookahead != blk + blk_len) return false;
 		const int bc = w.m.block_checksum_length;
 		const uint32_t block_max = uint32_t(w.m.frame_block_max);
@@ -191,7 +281,18 @@ private:
 		if (items.size() < 2) return false;
 		const size_t n = items.size();
 		const size_t span = items.back().off + size_t(items.back().len);
+		const double tb = dbg_now();
+		// the other staging buffer: the one just served from may still be read by the hash lane.  (The hash that read
+		// THIS buffer was queued a whole read-ahead ago.)
+		cur_ ^= 1;
+		if (hash_reads_[cur_]) {
+			if (lz4b200_event_sync(ctx_, hash_done_[cur_]) != LZ4B200_OK) return false;
+			hash_reads_[cur_] = false;
+		}
 		if (!reserve(span + 64, n * size_t(stride) + 64, n)) return false;
+		// the caller's bytes: a pinned copy serves the H2D (asynchronous for real) and the "same bytes again?" checks
+		memcpy(h_copy_, blk, span);
+		const double tc = dbg_now();
 		std::vector<lz4b200_blk_desc> descs(n);
 		for (size_t i = 0; i < n; i++) {
 			descs[i].src_off = items[i].off;
@@ -202,19 +303,23 @@ private:
 			descs[i].hist_avail = 0;
 		}
 		std::vector<lz4b200_blk_status> stats(n);
-		if (lz4b200_h2d(ctx_, d_src_, blk, span) != LZ4B200_OK ||
+		if (lz4b200_h2d(ctx_, d_src_, h_copy_, span) != LZ4B200_OK ||
 		    lz4b200_h2d(ctx_, d_desc_, descs.data(), sizeof(lz4b200_blk_desc) * n) != LZ4B200_OK ||
-		    lz4b200_decode_blocks(ctx_, d_src_, d_stage_, uint32_t(n), d_desc_, d_stat_) != LZ4B200_OK ||
+		    lz4b200_decode_blocks(ctx_, d_src_, d_stage_[cur_], uint32_t(n), d_desc_, d_stat_) != LZ4B200_OK ||
 		    lz4b200_d2h(ctx_, stats.data(), d_stat_, sizeof(lz4b200_blk_status) * n) != LZ4B200_OK ||
-		    lz4b200_d2h(ctx_, h_stage_, d_stage_, n * size_t(stride)) != LZ4B200_OK || lz4b200_sync(ctx_) != LZ4B200_OK)
+		    lz4b200_d2h(ctx_, h_stage_[cur_], d_stage_[cur_], n * size_t(stride)) != LZ4B200_OK)
 			return false;
+		const double td = dbg_now();
+		if (lz4b200_sync(ctx_) != LZ4B200_OK) return false;
+		const double te = dbg_now();
 		// keep the leading run of good blocks; the first one that is not (an error, or a block that reaches into
 		// its predecessor) and everything behind it take the one-block path when their turn comes
 		size_t good = 0;
 		while (good < n && stats[good].code == LZ4B200_ST_OK) good++;
 		if (good == 0) return false;
-		ahead_copy_.assign(blk, blk + items[good - 1].off + size_t(items[good - 1].len));
 		for (size_t i = 0; i < good; i++) ahead_.push_back({items[i].off, items[i].len, items[i].flags, uint32_t(i) * stride, stats[i]});
+		const double tf = dbg_now();
+		dbg_stage_[0] += tb - ta; dbg_stage_[1] += tc - tb; dbg_stage_[2] += td - tc; dbg_stage_[3] += te - td; dbg_stage_[4] += tf - te;
 		return true;
 	}
 
@@ -222,19 +327,26 @@ private:
 	{
 		if (src_bytes > cap_src_) {
 			if (d_src_) lz4b200_free(ctx_, d_src_);
-			d_src_ = nullptr;
+			if (h_copy_) lz4b200_free_host(ctx_, h_copy_);
+			d_src_ = h_copy_ = nullptr;
 			cap_src_ = 0;
-			if (lz4b200_alloc(ctx_, src_bytes, reinterpret_cast<void **>(&d_src_)) != LZ4B200_OK) return false;
+			if (lz4b200_alloc(ctx_, src_bytes, reinterpret_cast<void **>(&d_src_)) != LZ4B200_OK ||
+			    lz4b200_alloc_host(ctx_, src_bytes, reinterpret_cast<void **>(&h_copy_)) != LZ4B200_OK)
+				return false;
 			cap_src_ = src_bytes;
 		}
 		if (stage_bytes > cap_stage_) {
-			if (d_stage_) lz4b200_free(ctx_, d_stage_);
-			if (h_stage_) lz4b200_free_host(ctx_, h_stage_);
-			d_stage_ = h_stage_ = nullptr;
+			if (!join_hash_lane()) return false;   // (nobody reads what is about to be freed)
+			for (int k = 0; k < 2; k++) {
+				if (d_stage_[k]) lz4b200_free(ctx_, d_stage_[k]);
+				if (h_stage_[k]) lz4b200_free_host(ctx_, h_stage_[k]);
+				d_stage_[k] = h_stage_[k] = nullptr;
+			}
 			cap_stage_ = 0;
-			if (lz4b200_alloc(ctx_, stage_bytes, reinterpret_cast<void **>(&d_stage_)) != LZ4B200_OK ||
-			    lz4b200_alloc_host(ctx_, stage_bytes, reinterpret_cast<void **>(&h_stage_)) != LZ4B200_OK)
-				return false;
+			for (int k = 0; k < 2; k++)
+				if (lz4b200_alloc(ctx_, stage_bytes, reinterpret_cast<void **>(&d_stage_[k])) != LZ4B200_OK ||
+				    lz4b200_alloc_host(ctx_, stage_bytes, reinterpret_cast<void **>(&h_stage_[k])) != LZ4B200_OK)
+					return false;
 			cap_stage_ = stage_bytes;
 		}
 		if (n > cap_n_) {
@@ -253,8 +365,9 @@ private:
 
 	std::vector<Ahead> ahead_;
 	size_t ahead_pos_ = 0;
-	std::vector<uint8_t> ahead_copy_;
-	uint8_t *d_src_ = nullptr, *d_stage_ = nullptr, *h_stage_ = nullptr;
+	uint8_t *d_src_ = nullptr, *h_copy_ = nullptr;   // the Input bytes of the read-ahead, on the device and pinned on the host
+	uint8_t *d_stage_[2] = {nullptr, nullptr}, *h_stage_[2] = {nullptr, nullptr};   // decoded blocks, two buffers taking turns
+	int cur_ = 0;
 	lz4b200_blk_desc *d_desc_ = nullptr;
 	lz4b200_blk_status *d_stat_ = nullptr;
 	size_t cap_src_ = 0, cap_stage_ = 0, cap_n_ = 0;

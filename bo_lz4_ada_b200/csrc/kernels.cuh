@@ -230,15 +230,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // All 32 lanes call this together; ring = this warp's 8 x (8 * GROUP_BYTES + XXH_RING_PAD) bytes of shared memory.
 // Reads whole 16-byte granules: at most 19 bytes past p + n (the batch API's 32 bytes of slack cover it).
+// The stripes of a span through the ring: acc in, acc out (the chain itself; a caller with a running state -- the
+// content checksum under Update -- starts and finishes it elsewhere).
 template <uint32_t GROUP_BYTES>
-__device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
+__device__ __forceinline__ uint32_t quad_ring_stripes_t(const uint8_t *p, uint64_t nstripes, uint32_t acc, uint8_t *ring, int lane)
 {
 	constexpr uint32_t RING_BYTES = XXH_GROUPS * GROUP_BYTES;
 	constexpr uint32_t RING_STRIDE = RING_BYTES + XXH_RING_PAD;
 	constexpr uint32_t BATCH = GROUP_BYTES / 16;   // stripes per group
 	const int sub = lane & 3, q = lane >> 2;
 	uint8_t *my_ring = ring + q * RING_STRIDE;
-	const uint64_t nstripes = n >> 4;
 	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
 	const uint32_t mis = static_cast<uint32_t>(a & 15);
 	const uint8_t *abase = p - mis;                                   // 16-byte aligned
@@ -247,7 +248,6 @@ __device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64
 	const uint32_t my_groups = static_cast<uint32_t>((need + GROUP_BYTES - 1) / GROUP_BYTES);
 	const uint32_t max_groups = __reduce_max_sync(FULL_MASK, my_groups);
 	const uint32_t sh = (mis & 3) * 8;
-	uint32_t acc = xxh_init_acc(sub);
 
 	auto issue = [&](uint32_t g) {
 		if (g < my_groups) {
@@ -326,6 +326,14 @@ __device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64
 		if (g >= 1) issue(g - 1 + XXH_GROUPS);   // refill the slot batch g - 1 has just been read from
 	}
 	cp_async_wait<0>();
+	return acc;
+}
+
+template <uint32_t GROUP_BYTES>
+__device__ __forceinline__ uint32_t quad_xxh32_stream_t(const uint8_t *p, uint64_t n, uint8_t *ring, int lane)
+{
+	const uint64_t nstripes = n >> 4;
+	const uint32_t acc = quad_ring_stripes_t<GROUP_BYTES>(p, nstripes, xxh_init_acc(lane & 3), ring, lane);
 	const uint32_t a0 = __shfl_sync(FULL_MASK, acc, 0, 4);
 	const uint32_t a1 = __shfl_sync(FULL_MASK, acc, 1, 4);
 	const uint32_t a2 = __shfl_sync(FULL_MASK, acc, 2, 4);

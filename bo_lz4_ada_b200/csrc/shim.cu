@@ -861,21 +861,17 @@ xxh32_frames_kernel(const uint8_t *__restrict__ dst, uint32_t n_frames,
 
 // Streaming content checksum for the single-block path under Update: the XXH32 state lives in
 // device memory between blocks (XXHash32.Update, lib/lz4ada.adb:942-977).
-__global__ void __launch_bounds__(32)
-xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest,
-		    const lz4b200_blk_status *cond = nullptr)
+// ring: XXH_HUGE_RING_STRIDE bytes of shared memory -- the stripes run through the cp.async ring of K3 (quad 0 of the warp:
+// 16 KiB in flight, 2 GB/s) instead of register-staged loads (0.6 GB/s, which made the content checksum the slowest
+// part of the read-ahead path of Update).
+__device__ __forceinline__ void xxh_stream_update(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest, int lane,
+						   uint8_t *ring)
 {
-	// cond: the status of the block decoded just before on the same stream -- hash what it produced, or nothing if
-	// it failed (the host has not seen the status yet: no round trip between decode and hash)
-	if (cond) {
-		if (cond->code != LZ4B200_ST_OK) return;
-		len = cond->out_len;
-	}
-	const int lane = threadIdx.x & 31;
 	const int sub = lane & 3;
-	uint32_t acc = st->acc[sub];
-	uint32_t buf_size = st->buf_size;
-	const uint64_t total = st->total_len + len;
+	// (volatile: in the list kernel the state was written by other lanes of this warp a moment ago)
+	uint32_t acc = *reinterpret_cast<volatile uint32_t *>(&st->acc[sub]);
+	uint32_t buf_size = *reinterpret_cast<volatile uint32_t *>(&st->buf_size);
+	const uint64_t total = *reinterpret_cast<volatile uint64_t *>(&st->total_len) + len;
 	uint32_t pos = 0;
 	__syncwarp();
 	if (buf_size > 0 && len > 0) {
@@ -886,7 +882,7 @@ xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len
 		buf_size += take;
 		pos = take;
 		if (buf_size == 16) {
-			const uint8_t *bp = st->buf + 4 * sub;
+			const volatile uint8_t *bp = st->buf + 4 * sub;
 			const uint32_t x = bp[0] | (bp[1] << 8) | (bp[2] << 16) | (bp[3] << 24);
 			acc = xxh_round(acc, x);
 			buf_size = 0;
@@ -894,7 +890,10 @@ xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len
 		__syncwarp();
 	}
 	const uint32_t nstripes = (len - pos) >> 4;
-	acc = quad_stripes<true, true>(data + pos, nstripes, acc, sub);
+	{
+		const uint32_t mine = quad_ring_stripes_t<XXH_HUGE_GROUP_BYTES>(data + pos, lane < 4 ? nstripes : 0u, acc, ring, lane);
+		acc = __shfl_sync(FULL_MASK, mine, sub);   // the chain ran in lanes 0 .. 3
+	}
 	pos += nstripes << 4;
 	const uint32_t rem = len - pos;
 	if (rem > 0) {   // only reachable with buf_size == 0
@@ -913,6 +912,35 @@ xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len
 		const uint32_t h = xxh_finish<false>(a0, a1, a2, a3, total, st->buf, buf_size);
 		if (lane == 0) *digest = h;
 	}
+	__syncwarp();
+}
+
+__global__ void __launch_bounds__(32)
+xxh32_stream_kernel(XxhState *st, const uint8_t *__restrict__ data, uint32_t len, uint32_t *digest,
+		    const lz4b200_blk_status *cond = nullptr)
+{
+	// cond: the status of the block decoded just before on the same stream -- hash what it produced, or nothing if
+	// it failed (the host has not seen the status yet: no round trip between decode and hash)
+	if (cond) {
+		if (cond->code != LZ4B200_ST_OK) return;
+		len = cond->out_len;
+	}
+	__shared__ __align__(16) uint8_t ring[XXH_HUGE_RING_STRIDE];
+	xxh_stream_update(st, data, len, digest, threadIdx.x & 31, ring);
+}
+
+// ... the same over a list of pieces in stream order (the blocks a read-ahead of Update has served): one launch for
+// up to 255 blocks instead of one per block.  The list travels as a kernel parameter.
+struct PieceList {
+	uint32_t n;
+	uint32_t off[255];
+	uint32_t len[255];
+};
+__global__ void __launch_bounds__(32)
+xxh32_stream_list_kernel(XxhState *st, const uint8_t *__restrict__ base, const PieceList pl)
+{
+	__shared__ __align__(16) uint8_t ring[XXH_HUGE_RING_STRIDE];
+	for (uint32_t i = 0; i < pl.n; i++) xxh_stream_update(st, base + pl.off[i], pl.len[i], nullptr, threadIdx.x & 31, ring);
 }
 
 __global__ void xxh32_stream_reset_kernel(XxhState *st)
@@ -1415,6 +1443,13 @@ int lz4b200_event_record(lz4b200_ctx *ctx, void *event)
 	return LZ4B200_OK;
 }
 
+int lz4b200_event_sync(lz4b200_ctx *ctx, void *event)
+{
+	if (!ctx || !event) return LZ4B200_ERR_ARG;
+	CK(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+	return LZ4B200_OK;
+}
+
 int lz4b200_event_elapsed(lz4b200_ctx *ctx, void *start, void *stop, float *elapsed_ms)
 {
 	if (!ctx || !start || !stop || !elapsed_ms) return LZ4B200_ERR_ARG;
@@ -1845,6 +1880,52 @@ int lz4b200_stream_adopt(lz4b200_stream *s, const uint8_t *dev_bytes, uint32_t n
 	}
 	s->cursor += n;
 	s->frame_pos += n;
+	return LZ4B200_OK;
+}
+
+int lz4b200_stream_adopt_list(lz4b200_stream *s, const uint8_t *dev_base, uint32_t n_pieces, const uint32_t *offsets,
+			      const uint32_t *lengths, int hash_content)
+{
+	if (!s || n_pieces > 255 || (n_pieces && (!dev_base || !offsets || !lengths))) return LZ4B200_ERR_ARG;
+	if (n_pieces == 0) return LZ4B200_OK;
+	lz4b200_ctx *ctx = s->ctx;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n_pieces; i++) {
+		if (lengths[i] > s->max_block) return LZ4B200_ERR_ARG;
+		total += lengths[i];
+	}
+	if (total == 0) return LZ4B200_OK;
+	if (hash_content) {
+		PieceList pl;
+		pl.n = n_pieces;
+		memcpy(pl.off, offsets, sizeof(uint32_t) * n_pieces);
+		memcpy(pl.len, lengths, sizeof(uint32_t) * n_pieces);
+		xxh32_stream_list_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<XxhState *>(s->d_meta + META_XXH), dev_base, pl);
+		ctx->launches++;
+		CK(cudaGetLastError());
+	}
+	if (total >= HISTORY) {
+		// only the last 64 KiB can ever be referenced: they become the window
+		uint64_t need = HISTORY;
+		for (uint32_t i = n_pieces; i-- > 0 && need;) {
+			const uint64_t take = lengths[i] < need ? lengths[i] : need;
+			if (take) CK(cudaMemcpyAsync(s->d_win + need - take, dev_base + offsets[i] + lengths[i] - take, take, cudaMemcpyDeviceToDevice, ctx->stream));
+			need -= take;
+		}
+		s->cursor = HISTORY;
+	} else {
+		for (uint32_t i = 0; i < n_pieces; i++) {
+			const uint32_t n = lengths[i];
+			if (!n) continue;
+			if (s->cursor + n > s->win_size) {
+				CK(cudaMemcpyAsync(s->d_win, s->d_win + s->cursor - HISTORY, HISTORY, cudaMemcpyDeviceToDevice, ctx->stream));
+				s->cursor = HISTORY;
+			}
+			CK(cudaMemcpyAsync(s->d_win + s->cursor, dev_base + offsets[i], n, cudaMemcpyDeviceToDevice, ctx->stream));
+			s->cursor += n;
+		}
+	}
+	s->frame_pos += total;
 	return LZ4B200_OK;
 }
 

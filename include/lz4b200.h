@@ -205,6 +205,7 @@ int lz4b200_device_of(const lz4b200_ctx *ctx);
 int lz4b200_event_create(lz4b200_ctx *ctx, void **event);
 int lz4b200_event_destroy(lz4b200_ctx *ctx, void *event);
 int lz4b200_event_record(lz4b200_ctx *ctx, void *event);
+int lz4b200_event_sync(lz4b200_ctx *ctx, void *event);   /* the host waits until the lane has passed the record */
 int lz4b200_event_elapsed(lz4b200_ctx *ctx, void *start, void *stop, float *elapsed_ms);
 
 /* K1 (+K2): decode `n_blocks` mutually independent blocks, one warp per block,
@@ -293,6 +294,13 @@ int lz4b200_stream_digest(lz4b200_stream *s, uint32_t *xxh32);
  * running content checksum, exactly what lz4b200_stream_block does for a block it decodes itself.
  * Asynchronous on the context's current stream. */
 int lz4b200_stream_adopt(lz4b200_stream *s, const uint8_t *dev_bytes, uint32_t n, int hash_content);
+
+/* ... the same for up to 255 blocks at once, in stream order: piece i = lengths[i] bytes at dev_base + offsets[i].
+ * One hash launch for all of them (the running content checksum is one serial chain anyway) and the last 64 KiB as
+ * the new history window, instead of a copy and a launch per block.  Asynchronous on the stream's lane; the pieces
+ * must stay intact until the lane has passed them. */
+int lz4b200_stream_adopt_list(lz4b200_stream *s, const uint8_t *dev_base, uint32_t n_pieces, const uint32_t *offsets,
+		const uint32_t *lengths, int hash_content);
 
 /* ------------------------------------------------------------------------
  * LZ4Ada package API  (reference lib/lz4ada.ads)

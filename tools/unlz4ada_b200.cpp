@@ -8,6 +8,9 @@
 //   unlz4ada_b200 --update [-v]   the drop-in streaming API instead: Init + Update on 8 MiB reads, one block per call
 //                                 (tool_unlz4ada_simple/unlz4ada_simple.adb:23-36 with a bigger read)
 //   --file F --repeat N           read F instead of stdin, N passes in one process (the first pays for the CUDA context)
+//   --keep                        with --update --file --repeat: ONE decompressor for all passes (the file's frames N
+//                                 times over as concatenated frames): passes 2.. show the steady state of a long
+//                                 stream, without the device buffers a new decompressor allocates
 //   -v                            timing on stderr, I/O included: bytes in / out, seconds from the first read to the last
 //                                 write, decompressed MB/s; and the same without I/O
 //   exit 0: ok      exit 1: LZ4Ada exception (text on stderr, like GNAT's unhandled-exception line; the bytes decoded
@@ -25,12 +28,20 @@ static double now()
 	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int run_update(bool verbose, FILE *in_f, FILE *out_f)
+static lz4ada_decompressor *g_kept = nullptr;   // --keep
+static int g_kept_min = 0;
+
+static int run_update(bool verbose, FILE *in_f, FILE *out_f, bool keep = false)
 {
 	const double t0 = now();
 	int min_buffer_size = 0;
 	lz4ada_decompressor *ctx = nullptr;
-	if (lz4ada_init(&min_buffer_size, LZ4ADA_FOR_ALL, &ctx) != LZ4ADA_OK) return 3;
+	if (keep && g_kept) {
+		ctx = g_kept;
+		min_buffer_size = g_kept_min;
+	} else if (lz4ada_init(&min_buffer_size, LZ4ADA_FOR_ALL, &ctx) != LZ4ADA_OK) {
+		return 3;
+	}
 	std::vector<uint8_t> output(static_cast<size_t>(min_buffer_size));
 	std::vector<uint8_t> input(8u << 20);
 	size_t total_in = 0, total_out = 0;
@@ -60,7 +71,12 @@ static int run_update(bool verbose, FILE *in_f, FILE *out_f)
 		}
 	}
 	const int eof = lz4ada_is_end_of_frame(ctx);
-	lz4ada_free(ctx);
+	if (keep) {
+		g_kept = ctx;
+		g_kept_min = min_buffer_size;
+	} else {
+		lz4ada_free(ctx);
+	}
 	if (out_f) fflush(out_f);
 	if (verbose) {
 		const double dt = now() - t0;
@@ -129,12 +145,13 @@ static int run_batch(bool verbose, FILE *in_f, FILE *out_f)
 
 int main(int argc, char **argv)
 {
-	bool update = false, verbose = false;
+	bool update = false, verbose = false, keep = false;
 	const char *file = nullptr;
 	int repeat = 1;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--update")) update = true;
 		else if (!strcmp(argv[i], "-v")) verbose = true;
+		else if (!strcmp(argv[i], "--keep")) keep = true;
 		else if (!strcmp(argv[i], "--file") && i + 1 < argc) file = argv[++i];
 		else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
 		else {
@@ -150,8 +167,9 @@ int main(int argc, char **argv)
 		FILE *f = fopen(file, "rb");
 		if (!f) { perror(file); return 3; }
 		FILE *out_f = r + 1 == repeat ? stdout : nullptr;
-		rc = update ? run_update(verbose, f, out_f) : run_batch(verbose, f, out_f);
+		rc = update ? run_update(verbose, f, out_f, keep) : run_batch(verbose, f, out_f);
 		fclose(f);
 	}
+	if (g_kept) lz4ada_free(g_kept);
 	return rc;
 }
