@@ -63,6 +63,7 @@ public:
 			if (h_copy_) lz4b200_free_host(ctx_, h_copy_);
 			if (d_desc_) lz4b200_free(ctx_, d_desc_);
 			if (d_stat_) lz4b200_free(ctx_, d_stat_);
+			if (d_chain_) lz4b200_free(ctx_, d_chain_);
 			for (int k = 0; k < 2; k++)
 				if (h_stage_[k]) lz4b200_free_host(ctx_, h_stage_[k]);
 		}
@@ -303,9 +304,27 @@ private:
 			descs[i].hist_avail = 0;
 		}
 		std::vector<lz4b200_blk_status> stats(n);
+		// big blocks (>= 64 KiB of compressed bytes: a 1 - 4 MiB block) go to the chain kernel as chains of one, a CTA
+		// each (kernels_k7.cuh), instead of a warp each: 18 ms against 40 ms for a 4 MiB text block
+		bool big = false;
+		for (size_t i = 0; i < n; i++) big = big || (descs[i].src_len >= 65536u && !(descs[i].flags & LZ4B200_BLK_STORED));
+		std::vector<lz4b200_chain> chains;
+		if (big) {
+			chains.resize(n);
+			for (size_t i = 0; i < n; i++) {
+				descs[i].flags |= LZ4B200_BLK_CHAINED | LZ4B200_BLK_FIRST_OF_FRAME | LZ4B200_BLK_SOLO;
+				chains[i].first_block = uint32_t(i);
+				chains[i].n_blocks = 1;
+				chains[i].dst_off = descs[i].dst_off;
+				chains[i].dst_cap = descs[i].dst_cap;
+			}
+			if (lz4b200_h2d(ctx_, d_chain_, chains.data(), sizeof(lz4b200_chain) * n) != LZ4B200_OK) return false;
+		}
 		if (lz4b200_h2d(ctx_, d_src_, h_copy_, span) != LZ4B200_OK ||
 		    lz4b200_h2d(ctx_, d_desc_, descs.data(), sizeof(lz4b200_blk_desc) * n) != LZ4B200_OK ||
-		    lz4b200_decode_blocks(ctx_, d_src_, d_stage_[cur_], uint32_t(n), d_desc_, d_stat_) != LZ4B200_OK ||
+		    (big ? lz4b200_memset(ctx_, d_stat_, 0xff, sizeof(lz4b200_blk_status) * n) : LZ4B200_OK) != LZ4B200_OK ||
+		    (big ? lz4b200_decode_linked(ctx_, d_src_, d_stage_[cur_], uint32_t(n), d_chain_, d_desc_, d_stat_)
+			 : lz4b200_decode_blocks(ctx_, d_src_, d_stage_[cur_], uint32_t(n), d_desc_, d_stat_)) != LZ4B200_OK ||
 		    lz4b200_d2h(ctx_, stats.data(), d_stat_, sizeof(lz4b200_blk_status) * n) != LZ4B200_OK ||
 		    lz4b200_d2h(ctx_, h_stage_[cur_], d_stage_[cur_], n * size_t(stride)) != LZ4B200_OK)
 			return false;
@@ -352,11 +371,14 @@ private:
 		if (n > cap_n_) {
 			if (d_desc_) lz4b200_free(ctx_, d_desc_);
 			if (d_stat_) lz4b200_free(ctx_, d_stat_);
+			if (d_chain_) lz4b200_free(ctx_, d_chain_);
 			d_desc_ = nullptr;
 			d_stat_ = nullptr;
+			d_chain_ = nullptr;
 			cap_n_ = 0;
 			if (lz4b200_alloc(ctx_, sizeof(lz4b200_blk_desc) * n, reinterpret_cast<void **>(&d_desc_)) != LZ4B200_OK ||
-			    lz4b200_alloc(ctx_, sizeof(lz4b200_blk_status) * n, reinterpret_cast<void **>(&d_stat_)) != LZ4B200_OK)
+			    lz4b200_alloc(ctx_, sizeof(lz4b200_blk_status) * n, reinterpret_cast<void **>(&d_stat_)) != LZ4B200_OK ||
+			    lz4b200_alloc(ctx_, sizeof(lz4b200_chain) * n, reinterpret_cast<void **>(&d_chain_)) != LZ4B200_OK)
 				return false;
 			cap_n_ = n;
 		}
@@ -370,6 +392,7 @@ private:
 	int cur_ = 0;
 	lz4b200_blk_desc *d_desc_ = nullptr;
 	lz4b200_blk_status *d_stat_ = nullptr;
+	lz4b200_chain *d_chain_ = nullptr;
 	size_t cap_src_ = 0, cap_stage_ = 0, cap_n_ = 0;
 
 	Raised ensure_stream()
