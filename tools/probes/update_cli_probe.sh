@@ -14,6 +14,8 @@ open("/tmp/t64_4m.lz4", "wb").write(corpus.build_frame(plain, 7, False, True))
 open("/tmp/t64.bin", "wb").write(plain)
 PY
 for f in /tmp/t64.lz4 /tmp/t64l.lz4 /tmp/t64_4m.lz4 tests/golden/z9m.lz4; do
+  echo "== $f --update --keep (ONE decompressor for 4 passes: passes 2.. are the steady state of a long stream)"
+  ./tools/unlz4ada_b200 --update --keep -v --file $f --repeat 4 2>&1 >/dev/null | tail -3
   for mode in "--update" ""; do
     echo "== $f $mode (3 passes in one process; the first pays for the CUDA context)"
     ./tools/unlz4ada_b200 $mode -v --file $f --repeat 3 2>&1 >/tmp/out.bin | tail -3

@@ -5,7 +5,7 @@
 //
 //   unlz4ada_b200 [-v]            (default) the whole input goes to the batched device entry point in one call
 //                                 (lz4ada_batch_decompress: block table on the host, H2D, kernels, D2H) -- SURVEY.md 8f-1
-//   unlz4ada_b200 --update [-v]   the drop-in streaming API instead: Init + Update on 8 MiB reads, one block per call
+//   unlz4ada_b200 --update [-v]   the drop-in streaming API instead: Init + Update on 32 MiB reads, one block per call
 //                                 (tool_unlz4ada_simple/unlz4ada_simple.adb:23-36 with a bigger read)
 //   --file F --repeat N           read F instead of stdin, N passes in one process (the first pays for the CUDA context)
 //   --keep                        with --update --file --repeat: ONE decompressor for all passes (the file's frames N
@@ -43,7 +43,7 @@ static int run_update(bool verbose, FILE *in_f, FILE *out_f, bool keep = false)
 		return 3;
 	}
 	std::vector<uint8_t> output(static_cast<size_t>(min_buffer_size));
-	std::vector<uint8_t> input(8u << 20);
+	std::vector<uint8_t> input(32u << 20);   // big reads: the read-ahead decodes what is complete in one Input
 	size_t total_in = 0, total_out = 0;
 	double t_lib = 0;
 	for (;;) {
