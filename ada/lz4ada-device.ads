@@ -127,6 +127,10 @@ private package LZ4Ada.Device is
    --  become the stream's next bytes (history window + running content checksum)
    function Stream_Adopt (S : Stream; Dev_Bytes : System.Address; N : Unsigned_32; Hash_Content : int) return int
      with Import, Convention => C, External_Name => "lz4b200_stream_adopt";
+   --  ... up to 255 served blocks at once (Offsets / Lengths: arrays of Unsigned_32, pieces in stream order)
+   function Stream_Adopt_List (S : Stream; Dev_Base : System.Address; N_Pieces : Unsigned_32;
+                               Offsets, Lengths : System.Address; Hash_Content : int) return int
+     with Import, Convention => C, External_Name => "lz4b200_stream_adopt_list";
 
    --  which K1 kernel Decode_Blocks launches: 0 = chosen from the block count (v6 lane-per-block from ~20 000
    --  blocks on, v4 warp-per-block below); see include/lz4b200.h for the other values

@@ -1166,6 +1166,48 @@ def _run_chains_direct(ctx, chains_of_blocks, cap_per_block, checksums=False, co
     return res
 
 
+@pytest.mark.parametrize("sizes", [[5], [16, 1, 15, 17, 64], [65536] * 6 + [12345], [300000, 7, 65536, 200001], [1000] * 255])
+def test_stream_adopt_list_direct(ctx, sizes):
+    """lz4b200_stream_adopt_list (what Update's read-ahead hands the stream: up to 255 served blocks at once, one hash
+    launch through K3's ring): the running content checksum equals XXH32 of the pieces in order (lengths that are not
+    multiples of 16 exercise the carry between pieces), also when a second list follows; the per-block entry
+    lz4b200_stream_adopt gives the same digest."""
+    import ctypes
+    rng = np.random.default_rng(len(sizes) * 7 + sizes[0])
+    L = lz.lib()
+    stride = 300032
+    blob = bytearray(stride * len(sizes) + 64)
+    offs, whole = [], bytearray()
+    for i, n in enumerate(sizes):
+        piece = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        off = i * stride + (i % 7)          # every alignment
+        blob[off:off + n] = piece
+        offs.append(off)
+        whole += piece
+    d = ctx.alloc(len(blob))
+    ctx.h2d(d, bytes(blob))
+    digests = []
+    for mode in ("list", "list-twice", "single"):
+        st = ctypes.c_void_p()
+        assert L.lz4b200_stream_create(ctx.handle, 300000, ctypes.byref(st)) == 0
+        arr_o = (ctypes.c_uint32 * len(sizes))(*offs)
+        arr_n = (ctypes.c_uint32 * len(sizes))(*sizes)
+        if mode == "single":
+            for o, n in zip(offs, sizes):
+                assert L.lz4b200_stream_adopt(st, ctypes.c_void_p(d + o), n, 1) == 0
+        else:
+            for _ in range(2 if mode == "list-twice" else 1):
+                assert L.lz4b200_stream_adopt_list(st, ctypes.c_void_p(d), len(sizes), arr_o, arr_n, 1) == 0
+        h = ctypes.c_uint32(0)
+        assert L.lz4b200_stream_digest(st, ctypes.byref(h)) == 0
+        digests.append(h.value)
+        assert L.lz4b200_stream_destroy(st) == 0
+    ctx.free(d)
+    assert digests[0] == corpus.xxh32(bytes(whole))
+    assert digests[1] == corpus.xxh32(bytes(whole) * 2)
+    assert digests[2] == digests[0]
+
+
 def test_chain_kernel_shapes_direct(ctx):
     """The chain kernel (K7 by default) straight through lz4b200_decode_linked: the hand-made shapes of the K1 tests as
     chains of one block (dense 3-byte sequences, literal runs of 30 000 / 40 000 bytes -- longer than the staged bytes --
