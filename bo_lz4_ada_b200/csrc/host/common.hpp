@@ -171,5 +171,7 @@ lz4b200_ctx *default_context(Raised *why);
 
 // One host-layer object attached to a device context and freed with it (shim.cu): made on first use.
 void *ctx_attachment(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free_fn)(lz4b200_ctx *, void *));
+// ... and a second one (the batch scratch pool has the first, the streaming engine's buffer pool this one)
+void *ctx_attachment2(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free_fn)(lz4b200_ctx *, void *));
 
 }  // namespace lz4ada

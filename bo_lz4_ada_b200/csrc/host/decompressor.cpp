@@ -48,6 +48,46 @@ lz4b200_ctx *default_context(Raised *why)
 	return g_ctx;
 }
 
+// The read-ahead buffers of a streaming engine (device and pinned staging, tables, events).  A decompressor that is
+// freed leaves its set with the device context, the next one made on that context takes it over: pinned allocations
+// are what a new decompressor costs (~80 ms for the 64 MiB read-ahead), and a program that decompresses file after
+// file makes one per file.  Owned by the context (second attachment), freed with it.
+struct StageSet {
+	uint8_t *d_src = nullptr, *h_copy = nullptr;
+	uint8_t *d_stage[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr};
+	lz4b200_blk_desc *d_desc = nullptr;
+	lz4b200_blk_status *d_stat = nullptr;
+	lz4b200_chain *d_chain = nullptr;
+	void *hash_done[2] = {nullptr, nullptr};
+	size_t cap_src = 0, cap_stage = 0, cap_n = 0;
+};
+static void free_stage_set(lz4b200_ctx *ctx, StageSet &b)
+{
+	if (b.d_src) lz4b200_free(ctx, b.d_src);
+	if (b.h_copy) lz4b200_free_host(ctx, b.h_copy);
+	for (int k = 0; k < 2; k++) {
+		if (b.d_stage[k]) lz4b200_free(ctx, b.d_stage[k]);
+		if (b.h_stage[k]) lz4b200_free_host(ctx, b.h_stage[k]);
+		if (b.hash_done[k]) lz4b200_event_destroy(ctx, b.hash_done[k]);
+	}
+	if (b.d_desc) lz4b200_free(ctx, b.d_desc);
+	if (b.d_stat) lz4b200_free(ctx, b.d_stat);
+	if (b.d_chain) lz4b200_free(ctx, b.d_chain);
+	b = StageSet();
+}
+struct EnginePool {
+	std::mutex m;
+	bool has = false;
+	StageSet set;
+};
+static void *engine_pool_make(lz4b200_ctx *) { return new EnginePool(); }
+static void engine_pool_free(lz4b200_ctx *ctx, void *p)
+{
+	EnginePool *e = static_cast<EnginePool *>(p);
+	if (e->has) free_stage_set(ctx, e->set);
+	delete e;
+}
+
 // ---- streaming engine: one block at a time on the device ---------------------------------
 class DeviceStreamEngine : public BlockEngine {
 public:
@@ -55,17 +95,23 @@ public:
 	~DeviceStreamEngine() override
 	{
 		if (ctx_) {
-			if (d_src_) lz4b200_free(ctx_, d_src_);
-			for (int k = 0; k < 2; k++) {
-				if (d_stage_[k]) lz4b200_free(ctx_, d_stage_[k]);
-				if (hash_done_[k]) lz4b200_event_destroy(ctx_, hash_done_[k]);
+			join_hash_lane();   // nothing reads the staging buffers any more
+			StageSet mine;
+			mine.d_src = d_src_; mine.h_copy = h_copy_;
+			for (int k = 0; k < 2; k++) { mine.d_stage[k] = d_stage_[k]; mine.h_stage[k] = h_stage_[k]; mine.hash_done[k] = hash_done_[k]; }
+			mine.d_desc = d_desc_; mine.d_stat = d_stat_; mine.d_chain = d_chain_;
+			mine.cap_src = cap_src_; mine.cap_stage = cap_stage_; mine.cap_n = cap_n_;
+			EnginePool *pool = static_cast<EnginePool *>(ctx_attachment2(ctx_, engine_pool_make, engine_pool_free));
+			bool kept = false;
+			if (pool && (mine.cap_src || mine.cap_stage || mine.cap_n)) {
+				std::lock_guard<std::mutex> lock(pool->m);
+				if (!pool->has) {
+					pool->set = mine;
+					pool->has = true;
+					kept = true;
+				}
 			}
-			if (h_copy_) lz4b200_free_host(ctx_, h_copy_);
-			if (d_desc_) lz4b200_free(ctx_, d_desc_);
-			if (d_stat_) lz4b200_free(ctx_, d_stat_);
-			if (d_chain_) lz4b200_free(ctx_, d_chain_);
-			for (int k = 0; k < 2; k++)
-				if (h_stage_[k]) lz4b200_free_host(ctx_, h_stage_[k]);
+			if (!kept) free_stage_set(ctx_, mine);
 		}
 		if (getenv("LZ4ADA_UPDATE_DEBUG") && dbg_n_served_)
 			fprintf(stderr, "[lz4ada update] %ld read-aheads %.1f ms (scan %.1f, reserve %.1f, enqueue %.1f, sync %.1f, keep %.1f), %ld blocks served %.1f ms; all of block() %.1f ms, content checksums %.1f ms\n",
@@ -404,6 +450,18 @@ private:
 		if (lz4b200_stream_create(ctx_, max_block_, &stream_) != LZ4B200_OK) {
 			stream_ = nullptr;
 			return device_failure();
+		}
+		if (EnginePool *pool = static_cast<EnginePool *>(ctx_attachment2(ctx_, engine_pool_make, engine_pool_free))) {
+			std::lock_guard<std::mutex> lock(pool->m);
+			if (pool->has) {   // the buffers a decompressor freed earlier left behind
+				const StageSet &b = pool->set;
+				d_src_ = b.d_src; h_copy_ = b.h_copy;
+				for (int k = 0; k < 2; k++) { d_stage_[k] = b.d_stage[k]; h_stage_[k] = b.h_stage[k]; hash_done_[k] = b.hash_done[k]; }
+				d_desc_ = b.d_desc; d_stat_ = b.d_stat; d_chain_ = b.d_chain;
+				cap_src_ = b.cap_src; cap_stage_ = b.cap_stage; cap_n_ = b.cap_n;
+				pool->set = StageSet();
+				pool->has = false;
+			}
 		}
 		return ok();
 	}

@@ -1090,6 +1090,8 @@ struct lz4b200_ctx {
 	std::mutex attach_mutex;
 	void *attachment = nullptr;
 	void (*attachment_free)(lz4b200_ctx *, void *) = nullptr;
+	void *attachment2 = nullptr;   // a second host-layer object (the streaming engine's buffer pool)
+	void (*attachment2_free)(lz4b200_ctx *, void *) = nullptr;
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;      // the lane in use (lz4b200_use_lane)
@@ -1127,6 +1129,16 @@ void *ctx_attachment(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free
 		ctx->attachment_free = free_fn;
 	}
 	return ctx->attachment;
+}
+void *ctx_attachment2(lz4b200_ctx *ctx, void *(*make)(lz4b200_ctx *), void (*free_fn)(lz4b200_ctx *, void *))
+{
+	if (!ctx) return nullptr;
+	std::lock_guard<std::mutex> lock(ctx->attach_mutex);
+	if (!ctx->attachment2 && make) {
+		ctx->attachment2 = make(ctx);
+		ctx->attachment2_free = free_fn;
+	}
+	return ctx->attachment2;
 }
 }  // namespace lz4ada
 
@@ -1208,6 +1220,8 @@ int lz4b200_destroy(lz4b200_ctx *ctx)
 	cudaStreamSynchronize(ctx->lanes[0]);
 	if (ctx->attachment && ctx->attachment_free) ctx->attachment_free(ctx, ctx->attachment);
 	ctx->attachment = nullptr;
+	if (ctx->attachment2 && ctx->attachment2_free) ctx->attachment2_free(ctx, ctx->attachment2);
+	ctx->attachment2 = nullptr;
 	if (ctx->d_prof) {
 		static const char *names[v3::PROF_N] = {"load", "parse", "scan", "emit", "match", "flush", "exact", "blocks", "windows",
 							"iters", "fallback", "batches", "rounds", "early", "gatewait", "coop"};
