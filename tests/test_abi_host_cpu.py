@@ -293,3 +293,44 @@ def test_host_tools(oracle):
     assert "block max        262144" in out and "block checksum   True" in out and "block independ.  False" in out
     out = subprocess.run([sys.executable, tool, "hdrinfo"], input=_read("corruptedmagic.err"), capture_output=True).stdout.decode()
     assert out.strip() == MAN["error"]["corruptedmagic"]["eds"]
+
+
+def test_planner_places_few_big_blocks_as_chains_of_one():
+    """Big independent blocks (>= 64 KiB of compressed bytes) become chains of one (LZ4B200_BLK_SOLO | CHAINED |
+    FIRST_OF_FRAME) for the chain kernel while a batch holds few of them, and stay ordinary K1 blocks beyond the
+    limit (csrc/host/batch.cpp; LZ4B200_SOLO_MAX moves the limit, read once per process: a process each)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import bo_lz4_ada_b200 as lz
+from tools import corpus
+import test_abi_host_cpu as T
+text = corpus.text_like(700000, seed=3)
+frames = [corpus.build_frame(text[i * 1000:i * 1000 + 600000], 5, False, True) for i in range(3)]   # 256 KiB blocks: 2 big + 1 small each
+frames.append(corpus.build_frame(text[:200000], 4, False, True))                                       # 64 KiB blocks: never
+frames.append(corpus.build_frame(bytes(600000), 6, False, True))                                       # zeros: a few hundred compressed bytes
+b, _ = T._plan(frames)
+flags = [b.block_desc(i).flags for i in range(b.block_count)]
+sizes = [b.block_desc(i).src_len for i in range(b.block_count)]
+big = [i for i, n in enumerate(sizes) if n >= 65536]
+assert len(big) == 6, sizes
+solo = [i for i, f in enumerate(flags) if f & 32]
+print("solo", len(solo), "big", len(big))
+want = big if int(os.environ.get("LZ4B200_SOLO_MAX", "400")) >= len(big) and os.environ.get("LZ4B200_SOLO", "") != "0" else []
+assert solo == want, (solo, want)
+for i in solo:
+    assert flags[i] & 8 and flags[i] & 16            # CHAINED, FIRST_OF_FRAME: a chain of its own
+for i in range(len(flags)):
+    if i not in solo:
+        assert not flags[i] & 8                       # independent frames: nothing else is chained
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_extra, expect in (({}, "solo 6 big 6"), ({"LZ4B200_SOLO_MAX": "5"}, "solo 0 big 6"), ({"LZ4B200_SOLO": "0"}, "solo 0 big 6")):
+        env = dict(os.environ)
+        env.pop("LZ4B200_SOLO", None)
+        env.pop("LZ4B200_SOLO_MAX", None)
+        env.update(env_extra)
+        p = subprocess.run([sys.executable, "-c", code % (root, root)], capture_output=True, text=True, env=env, timeout=120)
+        assert p.returncode == 0 and expect in p.stdout, (env_extra, p.stdout[-300:], p.stderr[-1500:])
